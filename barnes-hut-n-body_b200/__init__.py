@@ -1,0 +1,12 @@
+"""B200-native Barnes–Hut physics step (drop-in for qwertukg/Barnes-Hut-N-Body's
+PhysicsEngine path).  The compute lives in csrc/ (hand-written sm_100a CUDA behind
+the C ABI of include/bh_engine.h); this package is the host-side mirror of the
+reference's Kotlin API plus scene generators.  No CPU fallback exists."""
+from ._abi import (BH_FLAG_BODY_COUNTS, BhConfig, BhCounters, BhError, BhParams, CudaLibraryMissing,
+                   CUDA_LIB_PATH, bind, load_cuda_library)
+from .engine import BHTree, Body, Config, NativeEngine, PhysicsEngine, Quad
+from . import scenes
+
+__all__ = ["BH_FLAG_BODY_COUNTS", "BhConfig", "BhCounters", "BhError", "BhParams", "CudaLibraryMissing",
+           "CUDA_LIB_PATH", "bind", "load_cuda_library", "BHTree", "Body", "Config", "NativeEngine",
+           "PhysicsEngine", "Quad", "scenes"]

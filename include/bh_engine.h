@@ -1,0 +1,192 @@
+/*
+ * bh_engine.h — C ABI of the Barnes–Hut physics-step engine (drop-in boundary).
+ *
+ * The reference (qwertukg/Barnes-Hut-N-Body) has no FFI of its own: the boundary
+ * is the Kotlin class API in BarnesHutAlg.kt that NBodyPanel.kt calls.  Every
+ * entry point below names the reference interface (file:line, paths relative to
+ * /root/reference/src/main/kotlin/) it replaces.  Two shared libraries export
+ * this ABI:
+ *
+ *   libbh_b200.so  — the product: hand-written sm_100a CUDA engine
+ *                    (barnes-hut-n-body_b200/csrc/).  No CPU fallback.
+ *   libbh_ref.so   — the oracle: literal f64 C++ restatement of BarnesHutAlg.kt
+ *                    (oracle/).  Test infrastructure + CPU baseline only.
+ *
+ * Conventions
+ *   - Every function returns an int status (BH_OK == 0, negative = error) unless
+ *     stated; nothing throws or aborts across the ABI.  bh_last_error() gives text.
+ *   - The caller owns all host arrays; they are only read/written during the call.
+ *   - State is SoA f64 (x, y, vx, vy, m), index = position in the reference's
+ *     `bodies` list (BarnesHutAlg.kt:295).  An output pointer may be NULL to skip it.
+ *   - An engine is single-owner, not re-entrant (the reference is driven from the
+ *     Swing EDT only: NBodyPanel.kt:106,290-293).  Calls block until complete.
+ */
+#ifndef BH_ENGINE_H
+#define BH_ENGINE_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BH_ABI_VERSION 1
+
+/* status codes */
+#define BH_OK             0
+#define BH_E_ARG         (-1)  /* bad argument / NULL handle                       */
+#define BH_E_CUDA        (-2)  /* CUDA runtime error (text in bh_last_error)       */
+#define BH_E_NCCL        (-3)  /* NCCL error / NCCL not loadable                   */
+#define BH_E_OOM         (-4)  /* host or device allocation failed                 */
+#define BH_E_STATE       (-5)  /* call not valid in the current engine state       */
+#define BH_E_UNSUPPORTED (-6)  /* not implemented by this library                  */
+
+/* bh_config.flags */
+#define BH_FLAG_BODY_COUNTS  1u  /* keep per-body interaction / opened-cell counts  */
+
+typedef struct bh_engine bh_engine;
+
+/* Engine construction parameters (no counterpart in the reference, whose engine
+ * is constructed from a body list only: BarnesHutAlg.kt:287). */
+typedef struct bh_config {
+    int32_t  struct_size;   /* sizeof(bh_config), for forward compatibility        */
+    int32_t  device;        /* CUDA device ordinal (ignored by the oracle)         */
+    int32_t  threads;       /* oracle: worker threads, 0 = all cores (:292,:377)   */
+    uint32_t flags;         /* BH_FLAG_*                                           */
+    int64_t  capacity_hint; /* bodies to pre-size buffers for (0 = grow on demand) */
+} bh_config;
+
+/* The values the reference reads live from `object Config` on every use
+ * (Config.kt:5-23; read sites BarnesHutAlg.kt:256,360-361,378,412,420) plus the
+ * two merge knobs (BarnesHutAlg.kt:315,321). */
+typedef struct bh_params {
+    double G;               /* Config.G        = 80.0  (Config.kt:11)              */
+    double dt;              /* Config.DT       = 0.005 (Config.kt:14)              */
+    double theta;           /* Config.theta    = 0.30  (Config.kt:23)              */
+    double soft2;           /* Config.SOFT2    = 1.0   (Config.kt:20)              */
+    double root_cx;         /* WIDTH_PX / 2.0           (BarnesHutAlg.kt:361)      */
+    double root_cy;         /* HEIGHT_PX / 2.0          (BarnesHutAlg.kt:361)      */
+    double root_half;       /* max(W,H) / 2.0 + 2.0     (BarnesHutAlg.kt:360)      */
+    double merge_max_mass;  /* PhysicsEngine.mergeMaxMass = 4000 (:315)            */
+    double merge_min_dist;  /* PhysicsEngine.mergeMinDist = 8.0  (:321); <=0 = off */
+} bh_params;
+
+/* Counters of the most recent force evaluation / build, and running totals.
+ * interaction = one pointForceAcc call (BarnesHutAlg.kt:220 or :230);
+ * opened      = one internal node that failed the test at :228;
+ * node visits of the reference walk = n_targets + 4*opened. */
+typedef struct bh_counters {
+    int64_t n_bodies;           /* bodies in the engine                             */
+    int64_t n_in_tree;          /* bodies inserted by the last build (:126 passed)  */
+    int64_t n_out_of_box;       /* bodies rejected by the root contains() test      */
+    int64_t n_jitter_bodies;    /* bodies that share a cell with h<1e-3 (:146)      */
+    int64_t n_cells;            /* internal + body-leaf cells of the last tree      */
+    int64_t n_internal;         /* internal cells of the last tree                  */
+    int32_t key_levels;         /* levels encoded in a Morton key (first h<1e-3)    */
+    int32_t max_depth;          /* deepest leaf of the last tree                    */
+    int64_t interactions;       /* last evaluation                                  */
+    int64_t opened;             /* last evaluation                                  */
+    int64_t exact_retests;      /* last evaluation: f64 re-tests of borderline MACs */
+    int64_t total_interactions; /* since bh_reset_counters                          */
+    int64_t total_opened;
+    int64_t total_evaluations;
+    int64_t total_steps;
+    int64_t total_merged;       /* bodies absorbed by the merge rule                */
+    double  ms_build;           /* device/host time of the phases, accumulated      */
+    double  ms_walk;            /*   since bh_reset_counters (CUDA events / clock)  */
+    double  ms_integrate;
+    double  ms_merge;
+    double  ms_comm;
+} bh_counters;
+
+/* ---- lifecycle ---------------------------------------------------------- */
+
+/* PhysicsEngine(initialBodies) constructor — BarnesHutAlg.kt:287-301. */
+int  bh_create(const bh_config* cfg, bh_engine** out);
+void bh_destroy(bh_engine* e);
+/* text of the last error on this engine (or of the last failed bh_create if e==NULL) */
+const char* bh_last_error(const bh_engine* e);
+/* "b200-cuda" or "reference-port"; lets a harness assert which library it loaded */
+const char* bh_backend_name(void);
+int  bh_abi_version(void);
+
+/* ---- parameters --------------------------------------------------------- */
+
+/* Fill *p with the reference defaults for a W x H window: Config.kt:5-23 and the
+ * root-box rule of buildTree(), BarnesHutAlg.kt:360-361. */
+int bh_default_params(int32_t width_px, int32_t height_px, bh_params* p);
+/* Snapshot of `Config` the next calls will use (the reference re-reads Config at
+ * every use; a façade calls this at the top of step()). */
+int bh_set_params(bh_engine* e, const bh_params* p);
+int bh_get_params(const bh_engine* e, bh_params* p);
+
+/* ---- state -------------------------------------------------------------- */
+
+/* resetBodies(newBodies) — BarnesHutAlg.kt:342-349 (and the constructor).  n may be 0. */
+int bh_set_bodies(bh_engine* e, int64_t n, const double* x, const double* y,
+                  const double* vx, const double* vy, const double* m);
+/* getBodies() — BarnesHutAlg.kt:335.  cap = capacity of the output arrays. */
+int bh_get_bodies(bh_engine* e, int64_t cap, double* x, double* y,
+                  double* vx, double* vy, double* m, int64_t* n_out);
+int64_t bh_num_bodies(const bh_engine* e);
+/* origin[k] = index, in the list given to the last bh_set_bodies, of the body now at
+ * position k.  Identity until the merge rule (BarnesHutAlg.kt:514-520) removes
+ * bodies; lets a façade write state back into the SAME Body objects the UI holds. */
+int bh_get_origin(bh_engine* e, int64_t cap, int32_t* origin, int64_t* n_out);
+/* render read-back used by NBodyPanel.paintComponent (NBodyPanel.kt:302-306):
+ * interleaved float (x,y) pairs and float masses. */
+int bh_get_positions_f32(bh_engine* e, int64_t cap, float* xy, float* m, int64_t* n_out);
+
+/* ---- compute ------------------------------------------------------------ */
+
+/* nsteps x PhysicsEngine.step() — BarnesHutAlg.kt:405-439: build+eval, half kick,
+ * drift, build+eval, half kick, merge rule (:463-532). */
+int bh_step(bh_engine* e, int32_t nsteps);
+/* buildTree() + computeAccelerations() on the current state, no integration —
+ * BarnesHutAlg.kt:359-366 + :374-395.  The parity entry point.  ax/ay: n doubles. */
+int bh_compute_accelerations(bh_engine* e, double* ax, double* ay);
+/* All-pairs direct sum with the same softened kernel (BarnesHutAlg.kt:250-259
+ * over every j != i, every body a source incl. out-of-box ones): accuracy oracle. */
+int bh_direct_sum(bh_engine* e, double* ax, double* ay);
+/* E = sum 1/2 m v^2  -  1/2 G sum_{i!=j} m_i m_j / sqrt(r_ij^2 + soft2); momentum. */
+int bh_energy(bh_engine* e, double* kinetic, double* potential, double* px, double* py);
+
+/* ---- introspection (parity artefacts) ----------------------------------- */
+
+/* After a build (bh_compute_accelerations / bh_step / bh_build_tree):
+ *   key[i]   Morton key of body i: `key_levels` 2-bit digits, MSB first, digit =
+ *            (x<cx?0:1)+(y<cy?0:2) at each level (BarnesHutAlg.kt:153-155);
+ *            UINT64_MAX for a body the root rejected (:126).
+ *   depth[i] depth of the leaf that holds body i (0 = root), -1 if not in the tree.
+ *   order[k] body index at sorted position k (in-tree bodies first, by key). */
+int bh_get_morton(bh_engine* e, uint64_t* key, int32_t* depth, int32_t* order);
+/* getTreeForDebug().visitQuads — BarnesHutAlg.kt:329-332, :265-274: DFS preorder
+ * over ALL cells incl. empty leaves, children in order 0..3.  body[k] = index of
+ * the body in a leaf, -1 for an empty leaf, -2 for an internal cell.  Pass cap=0
+ * to query *n_cells only. */
+int bh_get_tree(bh_engine* e, int64_t cap, int64_t* n_cells,
+                double* cx, double* cy, double* h,
+                double* mass, double* comx, double* comy, int32_t* body);
+/* buildTree() only (BarnesHutAlg.kt:359-366); what getTreeForDebug() triggers. */
+int bh_build_tree(bh_engine* e);
+int bh_get_counters(bh_engine* e, bh_counters* out);
+int bh_reset_counters(bh_engine* e);
+/* per-body counts of the last evaluation (needs BH_FLAG_BODY_COUNTS) */
+int bh_get_body_counts(bh_engine* e, int32_t* interactions, int32_t* opened);
+
+/* ---- multi-GPU: replicated tree, Morton-sliced targets (no reference
+ *      counterpart; the reference is single-process) ------------------------ */
+
+#define BH_COMM_ID_BYTES 128
+/* rank 0 creates an id and ships it to the other ranks (torch.distributed, a file…) */
+int bh_comm_unique_id(void* id_out, int32_t id_bytes);
+/* every rank: join a `world`-rank communicator; afterwards bh_step walks only this
+ * rank's slice of targets and all-gathers the drifted positions over NCCL. */
+int bh_comm_init(bh_engine* e, int32_t rank, int32_t world, const void* id, int32_t id_bytes);
+/* the slice [lo,hi) of home-ordered bodies rank `rank` of `world` owns */
+int bh_slice_bounds(int64_t n, int32_t world, int32_t rank, int64_t* lo, int64_t* hi);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BH_ENGINE_H */
