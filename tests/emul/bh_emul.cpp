@@ -1,0 +1,112 @@
+// bh_emul.cpp — TEST INFRASTRUCTURE: runs the engine's per-element algorithm core
+// (barnes-hut-n-body_b200/csrc/bh_core.h, the same inline functions the CUDA kernels call)
+// in serial loops on the CPU, so the key / layout / search / climb / criterion logic can be
+// checked against the oracle where no GPU exists.  It is NOT a product path: nothing under
+// barnes-hut-n-body_b200/ loads it, and the parallel primitives (onesweep sort, look-back
+// scan, atomics ordering) are only exercised by the real kernels in the `-m gpu` tests.
+#include <algorithm>
+#include <cstring>
+#include <numeric>
+#include <vector>
+#include "../../barnes-hut-n-body_b200/csrc/bh_core.h"
+#include "../../barnes-hut-n-body_b200/csrc/bh_export.h"
+
+struct Emul {
+    BhRoot root{};
+    int n = 0, n_in = 0, M = 0;
+    std::vector<uint64_t> key_by_body, keys;
+    std::vector<int> order, S, skip, parent, cnt, arrived;
+    std::vector<signed char> lvl;
+    std::vector<BhCellA> A;
+    std::vector<BhCellB> B;
+    std::vector<double> comx, comy, cmass;
+    BhTreeView view() {
+        BhTreeView t{};
+        t.keys = keys.data(); t.order = order.data(); t.S = S.data();
+        t.A = A.data(); t.B = B.data(); t.comx = comx.data(); t.comy = comy.data(); t.cmass = cmass.data();
+        t.skip = skip.data(); t.parent = parent.data(); t.cnt = cnt.data(); t.arrived = arrived.data();
+        t.lvl = lvl.data(); t.n_in = n_in; t.M = M;
+        return t;
+    }
+};
+
+static void build(Emul& e, int n, const double* x, const double* y, const double* m,
+                  double rcx, double rcy, double rhalf) {
+    e.root = BhRoot{rcx, rcy, rhalf, bh_key_levels(rhalf)};
+    e.n = n;
+    e.key_by_body.resize(n);
+    for (int b = 0; b < n; ++b)
+        e.key_by_body[b] = bh_root_contains(e.root, x[b], y[b]) ? bh_morton_key(e.root, x[b], y[b]) : BH_KEY_NOT_IN_TREE;
+    e.order.resize(n);
+    std::iota(e.order.begin(), e.order.end(), 0);
+    std::stable_sort(e.order.begin(), e.order.end(), [&](int a, int b) { return e.key_by_body[a] < e.key_by_body[b]; });
+    e.n_in = 0;
+    for (int b = 0; b < n; ++b) e.n_in += e.key_by_body[b] != BH_KEY_NOT_IN_TREE;
+    e.keys.resize(e.n_in);
+    for (int i = 0; i < e.n_in; ++i) e.keys[i] = e.key_by_body[e.order[i]];
+    e.S.assign(e.n_in + 1, 0);
+    for (int i = 0; i < e.n_in; ++i) {
+        const int dprev = i > 0 ? bh_common_levels(e.keys[i - 1], e.keys[i], e.root.levels) : -1;
+        const int dnext = i + 1 < e.n_in ? bh_common_levels(e.keys[i], e.keys[i + 1], e.root.levels) : -1;
+        e.S[i + 1] = e.S[i] + (dnext > dprev ? dnext - dprev : 0);
+    }
+    e.M = e.n_in + e.S[e.n_in];
+    e.skip.assign(e.M, 0); e.parent.assign(e.M, 0); e.cnt.assign(e.M, 0); e.arrived.assign(e.M, 0);
+    e.lvl.assign(e.M, 0); e.A.resize(e.M); e.B.resize(e.M);
+    e.comx.assign(e.M, 0); e.comy.assign(e.M, 0); e.cmass.assign(e.M, 0);
+    BhTreeView t = e.view();
+    for (int i = 0; i < e.n_in; ++i) bh_emit_body(t, e.root.levels, i);
+    for (int i = 0; i < e.n_in; ++i) { const int b = e.order[i]; bh_climb_body(t, e.root, i, x[b], y[b], m[b]); }
+}
+
+extern "C" {
+
+// One buildTree + computeAccelerations through the engine's algorithm core.
+// stats[0..5] = n_in, M, n_internal, interactions, opened, retests
+int bh_emul_accelerations(int n, const double* x, const double* y, const double* m,
+                          double rcx, double rcy, double rhalf, double theta, double soft2, double G,
+                          double* ax, double* ay, int32_t* cntI, int32_t* cntO,
+                          uint64_t* key_out, int32_t* depth_out, int32_t* order_out, int64_t* stats) {
+    Emul e;
+    build(e, n, x, y, m, rcx, rcy, rhalf);
+    BhTreeView t = e.view();
+    BhWalkParams w;
+    w.theta2 = theta * theta; w.soft2 = soft2; w.half = rhalf;
+    w.th2f = (float)w.theta2; w.soft2f = (float)soft2;
+    int64_t tI = 0, tO = 0, tR = 0;
+    for (int si = 0; si < n; ++si) {
+        const int b = e.order[si];
+        const int self = si < e.n_in ? e.S[si + 1] + si : -1;
+        BhWalkResult r = bh_walk_body(t, w, x[b], y[b], self);
+        if (ax) ax[b] = (m[b] == 0.0) ? NAN : G * (double)r.ax;
+        if (ay) ay[b] = (m[b] == 0.0) ? NAN : G * (double)r.ay;
+        if (cntI) cntI[b] = r.interactions;
+        if (cntO) cntO[b] = r.opened;
+        tI += r.interactions; tO += r.opened; tR += r.retests;
+    }
+    for (int b = 0; b < n; ++b) {
+        if (key_out) key_out[b] = e.key_by_body[b];
+        if (depth_out) depth_out[b] = -1;
+    }
+    for (int i = 0; i < e.n_in; ++i) if (depth_out) depth_out[e.order[i]] = e.lvl[e.S[i + 1] + i];
+    if (order_out) std::memcpy(order_out, e.order.data(), sizeof(int) * (size_t)n);
+    if (stats) { stats[0] = e.n_in; stats[1] = e.M; stats[2] = e.S[e.n_in]; stats[3] = tI; stats[4] = tO; stats[5] = tR; }
+    return 0;
+}
+
+// visitQuads-order export of the tree the core builds (same layout as bh_get_tree)
+int bh_emul_tree(int n, const double* x, const double* y, const double* m, double rcx, double rcy, double rhalf,
+                 int64_t cap, int64_t* n_cells, double* cx, double* cy, double* h, double* mass, double* comx,
+                 double* comy, int32_t* body) {
+    Emul e;
+    build(e, n, x, y, m, rcx, rcy, rhalf);
+    BhHostTree t{e.root, e.n_in, e.M, e.keys.data(), e.order.data(), e.S.data(), e.skip.data(), e.lvl.data(),
+                 e.comx.data(), e.comy.data(), e.cmass.data()};
+    BhCellsOut out;
+    out.cap = cap; out.cx = cx; out.cy = cy; out.h = h; out.mass = mass; out.comx = comx; out.comy = comy; out.body = body;
+    bh_export_cells(t, out);
+    if (n_cells) *n_cells = out.count;
+    return 0;
+}
+
+}  // extern "C"
