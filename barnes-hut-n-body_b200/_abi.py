@@ -46,7 +46,8 @@ class BhCounters(C.Structure):
                 ("total_interactions", C.c_int64), ("total_opened", C.c_int64),
                 ("total_evaluations", C.c_int64), ("total_steps", C.c_int64), ("total_merged", C.c_int64),
                 ("ms_build", C.c_double), ("ms_walk", C.c_double), ("ms_integrate", C.c_double),
-                ("ms_merge", C.c_double), ("ms_comm", C.c_double)]
+                ("ms_merge", C.c_double), ("ms_comm", C.c_double),
+                ("ms_step_call", C.c_double), ("kernel_launches", C.c_int64)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -87,6 +88,7 @@ SYMBOLS = {
     "bh_comm_unique_id": (C.c_int, [C.c_void_p, C.c_int32]),
     "bh_comm_init": (C.c_int, [_H, C.c_int32, C.c_int32, C.c_void_p, C.c_int32]),
     "bh_slice_bounds": (C.c_int, [C.c_int64, C.c_int32, C.c_int32, _I64, _I64]),
+    "bh_measure_fp32_tflops": (C.c_int, [C.c_int32, _D]),
 }
 
 

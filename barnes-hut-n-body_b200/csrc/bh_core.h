@@ -37,6 +37,10 @@
 #define BH_HD inline
 #endif
 
+#if !defined(__CUDACC__)
+struct float4 { float x, y, z, w; };   // host stand-in for the CUDA vector type
+#endif
+
 #define BH_MAX_LEVELS 31
 #define BH_KEY_NOT_IN_TREE 0xFFFFFFFFFFFFFFFFull
 // relative half-width of the band in which the FP32 opening test is re-done in FP64
@@ -170,12 +174,22 @@ BH_HD int bh_gallop_left(const uint64_t* __restrict__ keys, int from, uint64_t p
 // shift that isolates the first d digits of a key
 BH_HD int bh_prefix_shift(int levels, int d) { return 2 * (levels - d); }
 
-// ---- hot cell record read by the walk: two 16-byte vectors per cell ---------------------
-//   A = (comX_hi, comY_hi, mass, s2)   s2 = (cell side)^2 as float; -1 for a leaf or a
-//                                       zero-mass cell (always "accepted": BH.kt:216-221)
-//   B = (comX_lo, comY_lo, skip, level) skip/level are int bit patterns
-struct BhCellA { float xh, yh, m, s2; };
-struct BhCellB { float xl, yl; int skip; int level; };
+// ---- cell records -------------------------------------------------------------------------
+// Hot record read by the walk: ONE 32-byte sector per cell, loaded as two 16-byte vectors.
+//   (xh, yh, m, s2)         centre of mass (hi parts), mass, (cell side)^2 as float;
+//                           s2 = -1 for a leaf or a zero-mass cell: always "accepted"
+//                           (no opening test for leaves, zero mass is pruned: BH.kt:216-221)
+//   (xl, yl, skip, level)   lo parts; preorder position after the subtree; depth
+struct alignas(32) BhCell {
+    float xh, yh, m, s2;
+    float xl, yl;
+    int   skip, level;
+};
+// Exact record: f64 centre of mass and mass, bit-identical to BHTree.computeMass
+// (BH.kt:173-202).  Read by the climb, by borderline opening tests and by the export.
+struct alignas(32) BhCellD { double comx, comy, mass, pad; };
+// Skeleton written by bh_emit_body.
+struct alignas(16) BhCellS { int skip, parent, cnt, level; };
 
 // The reference's f64 opening test, BH.kt:223-228, bit-for-bit.
 BH_HD bool bh_exact_accept(double comx, double comy, double x, double y, double soft2, double theta2,
@@ -187,38 +201,45 @@ BH_HD bool bh_exact_accept(double comx, double comy, double x, double y, double 
     return s2 < BH_DMUL(theta2, dist2);
 }
 
-// ---- SoA view of the preorder cell arrays --------------------------------------------------
+// ---- view of the preorder cell arrays -------------------------------------------------------
 struct BhTreeView {
     const uint64_t* keys;   // sorted keys of the in-tree bodies            [n_in]
-    const int*      order;  // body (home) index at each sorted position     [n]
+    const int*      order;  // body index at each sorted position            [n]
     const int*      S;      // exclusive scan of cnt(i), S[n_in] = #internal [n_in+1]
-    BhCellA* A;             // hot record, first half                        [M]
-    BhCellB* B;             // hot record, second half                       [M]
-    double*  comx;          // f64 centre of mass / mass, bit-identical to   [M]
-    double*  comy;          //   BHTree.computeMass (BH.kt:173-202)
-    double*  cmass;
-    int*     skip;          // preorder position after the subtree           [M]
-    int*     parent;        // preorder position of the parent, -1 for root  [M]
-    int*     cnt;           // bodies below the cell                         [M]
+    BhCell*  cell;          // hot records                                   [M]
+    BhCellD* cd;            // exact f64 records                             [M]
+    BhCellS* sk;            // skeletons                                     [M]
     int*     arrived;       // climb counters, zero before the climb         [M]
-    signed char* lvl;       // depth of the cell                             [M]
     int n_in;               // bodies in the tree
     int M;                  // cells = n_in + #internal
 };
 
 #if defined(__CUDA_ARCH__)
-#define BH_ATOMIC_ADD_INT(p, v) atomicAdd((p), (v))
-#define BH_FENCE() __threadfence()
+// acq_rel RMW: releases this thread's child record, acquires the siblings' records
+__device__ __forceinline__ int bh_atomic_add_acq_rel(int* p, int v) {
+    int old;
+    asm volatile("atom.acq_rel.gpu.global.add.s32 %0, [%1], %2;" : "=r"(old) : "l"(p), "r"(v) : "memory");
+    return old;
+}
+#define BH_ATOMIC_ADD_INT(p, v) bh_atomic_add_acq_rel((p), (v))
 #define BH_LD_D(p) __ldcg(p)
-#define BH_LD_I(p) __ldcg(p)
-#define BH_RSQRTF(v) rsqrtf(v)
+// MUFU.RSQ without the denormal fix-up sequence (d2 >= soft2 is never subnormal)
+__device__ __forceinline__ float bh_rsqrt_ftz(float v) {
+    float r;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
+    return r;
+}
+#define BH_RSQRTF(v) bh_rsqrt_ftz(v)
+// an identity shuffle: stops ptxas from re-materialising the f64->f32 conversions in the loop
+#define BH_OPAQUE_F(v) (v) = __shfl_sync(0xffffffffu, (v), threadIdx.x & 31)
+#define BH_NOINLINE __noinline__
 #else
 static inline int bh_host_fetch_add(int* p, int v) { const int o = *p; *p = o + v; return o; }
 #define BH_ATOMIC_ADD_INT(p, v) bh_host_fetch_add((p), (v))
-#define BH_FENCE() ((void)0)
 #define BH_LD_D(p) (*(p))
-#define BH_LD_I(p) (*(p))
 #define BH_RSQRTF(v) (1.0f / sqrtf(v))
+#define BH_OPAQUE_F(v) ((void)0)
+#define BH_NOINLINE
 #endif
 
 // Skeleton of everything body i "owns" in the preorder array: the column of internal
@@ -244,122 +265,165 @@ BH_HD void bh_emit_body(const BhTreeView& t, int levels, int i) {
         const int sh = bh_prefix_shift(levels, d);
         hi = bh_gallop_right(t.keys, n, hi, k >> sh, sh);
         const int p = base + (d - dprev - 1);
-        t.skip[p] = t.S[hi + 1] + hi + 1;
-        t.cnt[p] = hi - i + 1;
-        t.parent[p] = (d == dprev + 1) ? headParent : (p - 1);
-        t.lvl[p] = (signed char)d;
+        BhCellS c;
+        c.skip = t.S[hi + 1] + hi + 1;
+        c.parent = (d == dprev + 1) ? headParent : (p - 1);
+        c.cnt = hi - i + 1;
+        c.level = d;
+        t.sk[p] = c;
     }
     const int lp = base + ncol;
-    t.skip[lp] = lp + 1;
-    t.cnt[lp] = 1;
-    t.parent[lp] = (ncol > 0) ? (lp - 1) : headParent;
-    t.lvl[lp] = (signed char)(((dprev > dnext) ? dprev : dnext) + 1);
+    BhCellS c;
+    c.skip = lp + 1;
+    c.parent = (ncol > 0) ? (lp - 1) : headParent;
+    c.cnt = 1;
+    c.level = ((dprev > dnext) ? dprev : dnext) + 1;
+    t.sk[lp] = c;
 }
 
-BH_HD void bh_write_cell(const BhTreeView& t, int p, double cx, double cy, double m, int level, bool leaf, double half) {
-    t.comx[p] = cx; t.comy[p] = cy; t.cmass[p] = m;
-    BhCellA a; BhCellB b;
-    bh_split(cx, &a.xh, &b.xl);
-    bh_split(cy, &a.yh, &b.yl);
-    a.m = (float)m;
-    // leaves and zero-mass cells are never opened (BH.kt:216-221): s2 = -1 always passes
-    a.s2 = (leaf || m == 0.0) ? -1.0f : (float)bh_side2(half, level);
-    b.skip = t.skip[p];
-    b.level = level;
-    t.A[p] = a; t.B[p] = b;
+BH_HD void bh_write_cell(const BhTreeView& t, int p, double cx, double cy, double m, int skip, int level, bool leaf,
+                         double half) {
+    BhCellD d; d.comx = cx; d.comy = cy; d.mass = m; d.pad = 0.0;
+    t.cd[p] = d;
+    BhCell c;
+    bh_split(cx, &c.xh, &c.xl);
+    bh_split(cy, &c.yh, &c.yl);
+    c.m = (float)m;
+    c.s2 = (leaf || m == 0.0) ? -1.0f : (float)bh_side2(half, level);
+    c.skip = skip;
+    c.level = level;
+    t.cell[p] = c;
 }
 
 // computeMass (BH.kt:173-202) bottom-up: the thread of body i writes its leaf, then climbs;
-// at each parent it adds the body count of the finished child and continues only if it
-// completed the parent (every child done) — the last arriver sums the children in child
-// order 0..3 (= preorder order), with the reference's exact f64 expression order.
+// at each parent it adds the body count of the finished child (one acq_rel atomic) and
+// continues only if that completed the parent — the last arriver sums the children in
+// child order 0..3 (= preorder order) with the reference's exact f64 expression order.
 BH_HD void bh_climb_body(const BhTreeView& t, const BhRoot& root, int i, double x, double y, double m) {
     int p = t.S[i + 1] + i;
-    bh_write_cell(t, p, x, y, m, t.lvl[p], true, root.half);
+    BhCellS s = t.sk[p];
+    bh_write_cell(t, p, x, y, m, s.skip, s.level, true, root.half);
     int carry = 1;
     for (;;) {
-        const int q = t.parent[p];
+        const int q = s.parent;
         if (q < 0) break;
-        BH_FENCE();
+        s = t.sk[q];
         const int old = BH_ATOMIC_ADD_INT(&t.arrived[q], carry);
-        if (old + carry != t.cnt[q]) break;
-        BH_FENCE();
+        if (old + carry != s.cnt) break;
         double mSum = 0.0, sx = 0.0, sy = 0.0;
-        const int end = t.skip[q];
-        for (int c = q + 1; c < end; c = t.skip[c]) {
-            const double mc = BH_LD_D(&t.cmass[c]);
+        for (int c = q + 1; c < s.skip; c = t.sk[c].skip) {
+            const double mc = BH_LD_D(&t.cd[c].mass);
             if (mc > 0.0) {   // BH.kt:189-192
                 mSum = BH_DADD(mSum, mc);
-                sx = BH_DADD(sx, BH_DMUL(BH_LD_D(&t.comx[c]), mc));
-                sy = BH_DADD(sy, BH_DMUL(BH_LD_D(&t.comy[c]), mc));
+                sx = BH_DADD(sx, BH_DMUL(BH_LD_D(&t.cd[c].comx), mc));
+                sy = BH_DADD(sy, BH_DMUL(BH_LD_D(&t.cd[c].comy), mc));
             }
         }
-        const int level = t.lvl[q];
         double cx, cy;
         if (mSum > 0.0) { cx = BH_DDIV(sx, mSum); cy = BH_DDIV(sy, mSum); }   // BH.kt:194-196
-        else { double h; bh_cell_geometry(root, t.keys[i], level, &cx, &cy, &h); }  // BH.kt:197-200
-        bh_write_cell(t, q, cx, cy, mSum, level, false, root.half);
-        carry = t.cnt[q];
+        else { double h; bh_cell_geometry(root, t.keys[i], s.level, &cx, &cy, &h); }  // BH.kt:197-200
+        bh_write_cell(t, q, cx, cy, mSum, s.skip, s.level, false, root.half);
+        carry = s.cnt;
         p = q;
     }
 }
 
 struct BhWalkParams {
-    float  th2f, soft2f;      // FP32 copies for the fast test
+    float  th2_lo, th2_hi;    // theta^2 * (1 -/+ guard band): FP32 sure-accept / sure-open bounds
+    float  soft2f;
     double theta2, soft2;     // BH.kt:378, Config.kt:20
     double half;              // root half-side
+    double side2[BH_MAX_LEVELS + 2];   // exact (2h)^2 per depth, BH.kt:226
 };
+
+BH_HD BhWalkParams bh_walk_params(double theta, double soft2, double half) {
+    BhWalkParams w;
+    w.theta2 = theta * theta;   // BH.kt:378
+    w.soft2 = soft2;
+    w.half = half;
+    w.th2_lo = (float)(w.theta2 * (1.0 - (double)BH_GUARD_BAND));
+    w.th2_hi = (float)(w.theta2 * (1.0 + (double)BH_GUARD_BAND));
+    w.soft2f = (float)soft2;
+    for (int d = 0; d < BH_MAX_LEVELS + 2; ++d) w.side2[d] = bh_side2(half, d);
+    return w;
+}
 
 struct BhWalkResult { double ax, ay; int interactions, opened, retests; };
 
+#ifndef BH_WALK_NEWTON
+#define BH_WALK_NEWTON 1      // one Newton step on MUFU.RSQ (device only)
+#endif
+
 // accumulateForce (BH.kt:215-239) for one body, stackless over the preorder array.
 // `self` = preorder position of the body's own leaf (-1 if it is not in the tree).
-// Per-body decisions are the reference's: FP32 test outside the guard band, the exact f64
-// expression inside it.  Interaction math is FP32 on (hi,lo)-split coordinate differences;
-// the FP32 partial sums are folded into f64 accumulators every 16 visits (all lanes of a
-// warp share the visit counter, so the fold is a uniform branch) — this removes the FP32
-// accumulation error, which otherwise dominates.
+// Per-body decisions are the reference's: the FP32 test decides outside a 1e-5 guard band,
+// the exact f64 expression inside it.  Interaction math is FP32 on (hi,lo)-split coordinate
+// differences; FP32 partial sums are folded into f64 accumulators every 16 visits (the lanes
+// of a warp share the visit counter, so the fold is a uniform branch).
 // Returns sum m*d/r^3 (G is applied by the caller).
+// ZERO_MASS = false skips the "mass != 0" test of the interaction counter (the host knows
+// whether any body has zero mass).
+template <bool ZERO_MASS>
 BH_HD BhWalkResult bh_walk_body(const BhTreeView& t, const BhWalkParams& w, double x, double y, int self) {
     float xh, xl, yh, yl;
     bh_split(x, &xh, &xl);
     bh_split(y, &yh, &yl);
+    BH_OPAQUE_F(xh); BH_OPAQUE_F(xl); BH_OPAQUE_F(yh); BH_OPAQUE_F(yl);   // keep the F2F out of the loop
     BhWalkResult r; r.ax = 0.0; r.ay = 0.0; r.interactions = 0; r.opened = 0; r.retests = 0;
-    const float ghi = 1.0f + BH_GUARD_BAND, glo = 1.0f - BH_GUARD_BAND;
     float fx = 0.f, fy = 0.f;
-    int p = 0, it = 0;
+    int p = 0;
     const int M = t.M;
+    const float4* __restrict__ cells = reinterpret_cast<const float4*>(t.cell);
     while (p < M) {
-        const BhCellA a = t.A[p];
-        const BhCellB b = t.B[p];
-        const float dx = (a.xh - xh) + (b.xl - xl);
-        const float dy = (a.yh - yh) + (b.yl - yl);
-        const float d2 = fmaf(dx, dx, fmaf(dy, dy, w.soft2f));
-        const float tt = w.th2f * d2;
-        bool accept = a.s2 * ghi < tt;
-        if (!accept && !(a.s2 * glo > tt)) {   // borderline: the reference's f64 test decides
-            accept = bh_exact_accept(t.comx[p], t.comy[p], x, y, w.soft2, w.theta2, w.half, b.level);
-            r.retests++;
-        }
-        if (accept) {
-            if (p != self) {
-                float inv = BH_RSQRTF(d2);
+#pragma unroll 1
+        for (int k = 0; k < 16; ++k) {
 #if defined(__CUDA_ARCH__)
-                inv = inv * fmaf(-0.5f * d2, inv * inv, 1.5f);   // one Newton step on MUFU.RSQ
+            const float4 a = __ldg(cells + 2 * (size_t)p);
+            const float4 b = __ldg(cells + 2 * (size_t)p + 1);
+            const int skip = __float_as_int(b.z);
+#else
+            const float4 a = cells[2 * (size_t)p];
+            const float4 b = cells[2 * (size_t)p + 1];
+            const int skip = t.cell[p].skip;
 #endif
-                const float wgt = a.m * inv * inv * inv;
-                fx = fmaf(wgt, dx, fx);
-                fy = fmaf(wgt, dy, fy);
-                r.interactions += (a.m != 0.0f);
+            const float dx = (a.x - xh) + (b.x - xl);
+            const float dy = (a.y - yh) + (b.y - yl);
+            const float d2 = fmaf(dx, dx, fmaf(dy, dy, w.soft2f));
+            bool accept = a.w < d2 * w.th2_lo;
+            if (!accept && !(a.w > d2 * w.th2_hi)) {   // borderline: the reference's f64 test decides
+#if defined(__CUDA_ARCH__)
+                const int level = __float_as_int(b.w);
+#else
+                const int level = t.cell[p].level;
+#endif
+                // BH.kt:223-228 bit-for-bit (f64, no contraction)
+                const BhCellD e = t.cd[p];
+                const double ex = BH_DSUB(e.comx, x), ey = BH_DSUB(e.comy, y);
+                const double dist2 = BH_DADD(BH_DADD(BH_DMUL(ex, ex), BH_DMUL(ey, ey)), w.soft2);
+                accept = w.side2[level] < BH_DMUL(w.theta2, dist2);
+                r.retests++;
             }
-            p = b.skip;
-        } else {
-            r.opened++;
-            p = p + 1;
+            if (accept) {
+                if (p != self) {
+                    float inv = BH_RSQRTF(d2);
+#if defined(__CUDA_ARCH__) && BH_WALK_NEWTON
+                    inv = inv * fmaf(-0.5f * d2, inv * inv, 1.5f);
+#endif
+                    const float wgt = a.z * inv * inv * inv;
+                    fx = fmaf(wgt, dx, fx);
+                    fy = fmaf(wgt, dy, fy);
+                    r.interactions += ZERO_MASS ? (a.z != 0.0f) : 1;
+                }
+                p = skip;
+            } else {
+                r.opened++;
+                p = p + 1;
+            }
+            if (p >= M) break;
         }
-        if ((++it & 15) == 0) { r.ax += (double)fx; r.ay += (double)fy; fx = 0.f; fy = 0.f; }
+        // every lane of a warp is at the same k: the fold is a uniform branch
+        r.ax += (double)fx; r.ay += (double)fy; fx = 0.f; fy = 0.f;
     }
-    r.ax += (double)fx; r.ay += (double)fy;
     return r;
 }
 

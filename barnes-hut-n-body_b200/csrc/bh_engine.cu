@@ -188,6 +188,7 @@ __global__ void __launch_bounds__(256) k_climb(BhTreeView t, BhRoot root, const 
 
 // accumulateForce (BH.kt:215-239) + ax = fx/m (BH.kt:390-391): one thread per target body,
 // Morton-adjacent bodies in a warp, stackless over the preorder cells.
+template <bool ZERO_MASS>
 __global__ void __launch_bounds__(128)
 k_walk(BhTreeView t, BhWalkParams w, int first_target, int n_targets, const double* __restrict__ x,
        const double* __restrict__ y, const double* __restrict__ m, double G, double* __restrict__ ax,
@@ -195,11 +196,15 @@ k_walk(BhTreeView t, BhWalkParams w, int first_target, int n_targets, const doub
        DevTotals* __restrict__ tot) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     int ni = 0, no = 0, nr = 0;
-    if (k < n_targets) {
-        const int si = first_target + k;
-        const int b = t.order[si];
-        const int self = (si < t.n_in) ? (t.S[si + 1] + si) : -1;
-        const BhWalkResult r = bh_walk_body(t, w, x[b], y[b], self);
+    // every lane enters the walk (it contains full-warp shuffles); surplus lanes see an empty tree
+    const bool active = k < n_targets;
+    const int si = first_target + (active ? k : 0);
+    const int b = t.order[si];
+    const int self = (si < t.n_in) ? (t.S[si + 1] + si) : -1;
+    BhTreeView tv = t;
+    if (!active) tv.M = 0;
+    const BhWalkResult r = bh_walk_body<ZERO_MASS>(tv, w, x[b], y[b], self);
+    if (active) {
         const double mb = m[b];
         // BH.kt:390-391 divides the force by b.m: a zero-mass body gets 0/0 = NaN
         ax[b] = (mb == 0.0) ? nan("") : G * r.ax;
@@ -339,7 +344,21 @@ __global__ void k_positions_f32(const double* __restrict__ x, const double* __re
 __global__ void k_leaf_depth(BhTreeView t, int n, int* __restrict__ depth) {
     const int si = blockIdx.x * blockDim.x + threadIdx.x;
     if (si >= n) return;
-    depth[t.order[si]] = (si < t.n_in) ? (int)t.lvl[t.S[si + 1] + si] : -1;
+    depth[t.order[si]] = (si < t.n_in) ? t.sk[t.S[si + 1] + si].level : -1;
+}
+
+// register-only FFMA throughput probe: 8 independent chains per thread
+__global__ void __launch_bounds__(256) k_fp32_peak(float* out, int iters, float a, float b) {
+    float v0 = threadIdx.x, v1 = v0 + 1.f, v2 = v0 + 2.f, v3 = v0 + 3.f, v4 = v0 + 4.f, v5 = v0 + 5.f, v6 = v0 + 6.f, v7 = v0 + 7.f;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            v0 = fmaf(v0, a, b); v1 = fmaf(v1, a, b); v2 = fmaf(v2, a, b); v3 = fmaf(v3, a, b);
+            v4 = fmaf(v4, a, b); v5 = fmaf(v5, a, b); v6 = fmaf(v6, a, b); v7 = fmaf(v7, a, b);
+        }
+    }
+    const float s = v0 + v1 + v2 + v3 + v4 + v5 + v6 + v7;
+    if (s == 12345.678f) out[0] = s;   // never true; keeps the chains alive
 }
 
 thread_local std::string g_create_err;
@@ -362,7 +381,7 @@ struct bh_engine {
     bh_params par{};
     int device = 0, num_sms = 148;
     cudaStream_t st = nullptr;
-    cudaEvent_t ev[12]{};   // [0..3] evaluation A, [4..7] evaluation B, [8..9] whole step
+    cudaEvent_t ev[12]{};   // [0..3] evaluation A, [4..7] evaluation B, [8..9] whole step, [10..11] whole call
     std::string err;
 
     // body state, f64 SoA, index = position in the reference's `bodies` list
@@ -370,6 +389,7 @@ struct bh_engine {
     double *x = nullptr, *y = nullptr, *vx = nullptr, *vy = nullptr, *m = nullptr, *ax = nullptr, *ay = nullptr;
     int *cntI = nullptr, *cntO = nullptr;
     std::vector<int32_t> origin;
+    bool any_zero_mass = false;   // some body has m == 0 (zero-mass cells are pruned, BH.kt:216)
 
     // sort buffers + scratch (scalars | sort scratch | scan status) zeroed per build
     uint64_t *keys_a = nullptr, *keys_b = nullptr;
@@ -384,10 +404,10 @@ struct bh_engine {
     // tree
     int* S = nullptr;
     int64_t cell_cap = 0;
-    BhCellA* A = nullptr; BhCellB* B = nullptr;
-    double *comx = nullptr, *comy = nullptr, *cmass = nullptr;
-    int *skip = nullptr, *parent = nullptr, *cnt = nullptr, *arrived = nullptr;
-    signed char* lvl = nullptr;
+    BhCell* cell = nullptr;      // hot 32 B records
+    BhCellD* cd = nullptr;       // exact f64 records
+    BhCellS* sk = nullptr;       // skeletons
+    int* arrived = nullptr;
 
     bool tree_valid = false;
     BhRoot root{};
@@ -415,8 +435,7 @@ struct bh_engine {
         cap = 0;
     }
     void free_cells() {
-        dev_free(A); dev_free(B); dev_free(comx); dev_free(comy); dev_free(cmass);
-        dev_free(skip); dev_free(parent); dev_free(cnt); dev_free(arrived); dev_free(lvl);
+        dev_free(cell); dev_free(cd); dev_free(sk); dev_free(arrived);
         cell_cap = 0;
     }
 
@@ -447,10 +466,8 @@ struct bh_engine {
         if (mm >= (int64_t)1 << 31) return fail(BH_E_ARG, "tree has more than 2^31 cells");
         const int64_t c = std::max<int64_t>(mm + mm / 8, 2048);
         free_cells();
-        BH_TRY(dev_alloc(&A, c)); BH_TRY(dev_alloc(&B, c));
-        BH_TRY(dev_alloc(&comx, c)); BH_TRY(dev_alloc(&comy, c)); BH_TRY(dev_alloc(&cmass, c));
-        BH_TRY(dev_alloc(&skip, c)); BH_TRY(dev_alloc(&parent, c)); BH_TRY(dev_alloc(&cnt, c));
-        BH_TRY(dev_alloc(&arrived, c)); BH_TRY(dev_alloc(&lvl, c));
+        BH_TRY(dev_alloc(&cell, c)); BH_TRY(dev_alloc(&cd, c)); BH_TRY(dev_alloc(&sk, c));
+        BH_TRY(dev_alloc(&arrived, c));
         cell_cap = c;
         return BH_OK;
     }
@@ -458,8 +475,7 @@ struct bh_engine {
     BhTreeView view() const {
         BhTreeView t{};
         t.keys = keys_sorted; t.order = order; t.S = S;
-        t.A = A; t.B = B; t.comx = comx; t.comy = comy; t.cmass = cmass;
-        t.skip = skip; t.parent = parent; t.cnt = cnt; t.arrived = arrived; t.lvl = lvl;
+        t.cell = cell; t.cd = cd; t.sk = sk; t.arrived = arrived;
         t.n_in = n_in; t.M = M;
         return t;
     }
@@ -484,6 +500,7 @@ struct bh_engine {
             keys_sorted = where ? keys_b : keys_a;
             order = reinterpret_cast<const int*>(where ? vals_b : vals_a);
             k_count_scan<<<(nn + SCAN_TILE - 1) / SCAN_TILE, SCAN_THREADS, 0, st>>>(keys_sorted, root.levels, sc(), S, scan_status);
+            ctr.kernel_launches += 4 + passes;   // keygen, histogram, histogram_scan, passes, count_scan
         }
         BH_TRY(cudaMemcpyAsync(sc_host, sc(), sizeof(DevScalars), cudaMemcpyDeviceToHost, st));
         BH_TRY(cudaStreamSynchronize(st));
@@ -497,6 +514,7 @@ struct bh_engine {
             const BhTreeView t = view();
             k_emit<<<(n_in + 255) / 256, 256, 0, st>>>(t, root.levels);
             k_climb<<<(n_in + 255) / 256, 256, 0, st>>>(t, root, x, y, m);
+            ctr.kernel_launches += 2;
         }
         BH_TRY(cudaEventRecord(ev[slot + 1], st));
         BH_TRY(cudaGetLastError());
@@ -534,13 +552,12 @@ struct bh_engine {
     int walk(int first, int count, int slot = 0) {
         BH_TRY(cudaEventRecord(ev[slot + 2], st));
         if (count > 0) {
-            BhWalkParams w;
-            w.theta2 = par.theta * par.theta;   // BH.kt:378
-            w.soft2 = par.soft2;
-            w.half = par.root_half;
-            w.th2f = (float)w.theta2;
-            w.soft2f = (float)par.soft2;
-            k_walk<<<(count + 127) / 128, 128, 0, st>>>(view(), w, first, count, x, y, m, par.G, ax, ay, cntI, cntO, sc(), tot);
+            const BhWalkParams w = bh_walk_params(par.theta, par.soft2, par.root_half);
+            if (any_zero_mass)
+                k_walk<true><<<(count + 127) / 128, 128, 0, st>>>(view(), w, first, count, x, y, m, par.G, ax, ay, cntI, cntO, sc(), tot);
+            else
+                k_walk<false><<<(count + 127) / 128, 128, 0, st>>>(view(), w, first, count, x, y, m, par.G, ax, ay, cntI, cntO, sc(), tot);
+            ctr.kernel_launches += 1;
         }
         BH_TRY(cudaEventRecord(ev[slot + 3], st));
         BH_TRY(cudaGetLastError());
@@ -576,7 +593,7 @@ struct bh_engine {
     }
 
     int kick(double dtHalf, double dt, int drift) {
-        if (n > 0) k_kick_drift<<<((int)n + 255) / 256, 256, 0, st>>>(0, (int)n, x, y, vx, vy, ax, ay, dtHalf, dt, drift);
+        if (n > 0) { k_kick_drift<<<((int)n + 255) / 256, 256, 0, st>>>(0, (int)n, x, y, vx, vy, ax, ay, dtHalf, dt, drift); ctr.kernel_launches += 1; }
         BH_TRY(cudaGetLastError());
         return BH_OK;
     }
@@ -701,6 +718,8 @@ int bh_set_bodies(bh_engine* e, int64_t n, const double* x, const double* y, con
     e->n = n;
     e->tree_valid = false;
     e->heavies_valid = false;
+    e->any_zero_mass = false;
+    for (int64_t i = 0; i < n; ++i) if (m[i] == 0.0) { e->any_zero_mass = true; break; }
     try {
         e->origin.resize((size_t)n);
         for (int64_t i = 0; i < n; ++i) e->origin[(size_t)i] = (int32_t)i;
@@ -756,6 +775,7 @@ int bh_get_positions_f32(bh_engine* e, int64_t cap, float* xy, float* m, int64_t
 int bh_step(bh_engine* e, int32_t nsteps) {
     if (!e || nsteps < 0) return e ? e->fail(BH_E_ARG, "bh_step: bad arguments") : BH_E_ARG;
     E_TRY(cudaSetDevice(e->device));
+    E_TRY(cudaEventRecord(e->ev[10], e->st));
     for (int s = 0; s < nsteps; ++s) {
         E_TRY(cudaEventRecord(e->ev[8], e->st));
         if (int rc = e->step_once()) return rc;
@@ -766,7 +786,10 @@ int bh_step(bh_engine* e, int32_t nsteps) {
         // kick/drift (+ merge) = whole step minus the build and walk phases
         if (cudaEventElapsedTime(&total, e->ev[8], e->ev[9]) == cudaSuccess && total > phases) e->ctr.ms_integrate += total - phases;
     }
-    if (nsteps == 0) return e->finish();
+    E_TRY(cudaEventRecord(e->ev[11], e->st));
+    if (int rc = e->finish()) return rc;
+    float call_ms = 0.f;
+    if (cudaEventElapsedTime(&call_ms, e->ev[10], e->ev[11]) == cudaSuccess) e->ctr.ms_step_call = call_ms;
     return BH_OK;
 }
 
@@ -863,21 +886,17 @@ int bh_get_tree(bh_engine* e, int64_t cap, int64_t* n_cells, double* cx, double*
     try {
         const size_t M = (size_t)e->M, ni = (size_t)e->n_in;
         std::vector<uint64_t> keys(ni);
-        std::vector<int> order(ni), S(ni + 1), skip(M);
-        std::vector<signed char> lvl(M);
-        std::vector<double> hx(M), hy(M), hm(M);
+        std::vector<int> order(ni), S(ni + 1);
+        std::vector<BhCellS> sk(M);
+        std::vector<BhCellD> cd(M);
         if (ni) {
             E_TRY(cudaMemcpy(keys.data(), e->keys_sorted, ni * 8, cudaMemcpyDeviceToHost));
             E_TRY(cudaMemcpy(order.data(), e->order, ni * 4, cudaMemcpyDeviceToHost));
             E_TRY(cudaMemcpy(S.data(), e->S, (ni + 1) * 4, cudaMemcpyDeviceToHost));
-            E_TRY(cudaMemcpy(skip.data(), e->skip, M * 4, cudaMemcpyDeviceToHost));
-            E_TRY(cudaMemcpy(lvl.data(), e->lvl, M, cudaMemcpyDeviceToHost));
-            E_TRY(cudaMemcpy(hx.data(), e->comx, M * 8, cudaMemcpyDeviceToHost));
-            E_TRY(cudaMemcpy(hy.data(), e->comy, M * 8, cudaMemcpyDeviceToHost));
-            E_TRY(cudaMemcpy(hm.data(), e->cmass, M * 8, cudaMemcpyDeviceToHost));
+            E_TRY(cudaMemcpy(sk.data(), e->sk, M * sizeof(BhCellS), cudaMemcpyDeviceToHost));
+            E_TRY(cudaMemcpy(cd.data(), e->cd, M * sizeof(BhCellD), cudaMemcpyDeviceToHost));
         }
-        BhHostTree t{e->root, e->n_in, e->M, keys.data(), order.data(), S.data(), skip.data(), lvl.data(),
-                     hx.data(), hy.data(), hm.data()};
+        BhHostTree t{e->root, e->n_in, e->M, keys.data(), order.data(), S.data(), sk.data(), cd.data()};
         BhCellsOut out;
         out.cap = cap; out.cx = cx; out.cy = cy; out.h = h; out.mass = mass; out.comx = comx; out.comy = comy; out.body = body;
         bh_export_cells(t, out);
@@ -904,6 +923,7 @@ int bh_reset_counters(bh_engine* e) {
     e->ctr.n_in_tree = keep.n_in_tree; e->ctr.n_out_of_box = keep.n_out_of_box; e->ctr.n_cells = keep.n_cells;
     e->ctr.n_internal = keep.n_internal; e->ctr.key_levels = keep.key_levels; e->ctr.max_depth = keep.max_depth;
     e->ctr.n_jitter_bodies = keep.n_jitter_bodies;
+    e->ctr.ms_step_call = keep.ms_step_call;
     return BH_OK;
 }
 
@@ -923,6 +943,32 @@ int bh_slice_bounds(int64_t n, int32_t world, int32_t rank, int64_t* lo, int64_t
     const int64_t per = (n + world - 1) / world;
     *lo = std::min<int64_t>(n, per * rank);
     *hi = std::min<int64_t>(n, per * (rank + 1));
+    return BH_OK;
+}
+
+int bh_measure_fp32_tflops(int32_t device, double* tflops) {
+    if (!tflops) return BH_E_ARG;
+    if (cudaSetDevice(device) != cudaSuccess) return BH_E_CUDA;
+    int sms = 0;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    float* d = nullptr;
+    cudaEvent_t a, b;
+    if (cudaMalloc(&d, 4) != cudaSuccess || cudaEventCreate(&a) != cudaSuccess || cudaEventCreate(&b) != cudaSuccess) return BH_E_CUDA;
+    const int blocks = sms * 8, iters = 4096;
+    double best = 0.0;
+    for (int rep = 0; rep < 4; ++rep) {
+        cudaEventRecord(a);
+        k_fp32_peak<<<blocks, 256>>>(d, iters, 1.0001f, 0.5f);
+        cudaEventRecord(b);
+        cudaEventSynchronize(b);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, a, b);
+        const double fl = 2.0 * 64.0 * (double)iters * 256.0 * blocks;
+        if (ms > 0.f) best = std::max(best, fl / (ms * 1e-3) / 1e12);
+    }
+    cudaEventDestroy(a); cudaEventDestroy(b); cudaFree(d);
+    if (cudaGetLastError() != cudaSuccess) return BH_E_CUDA;
+    *tflops = best;
     return BH_OK;
 }
 

@@ -16,9 +16,8 @@ struct BhHostTree {
     const uint64_t* keys;     // [n_in] sorted
     const int* order;         // [n_in] body index per sorted position
     const int* S;             // [n_in+1]
-    const int* skip;          // [M]
-    const signed char* lvl;   // [M]
-    const double *comx, *comy, *cmass;  // [M]
+    const BhCellS* sk;        // [M] skeletons
+    const BhCellD* cd;        // [M] exact f64 records
 };
 
 struct BhCellsOut {
@@ -50,19 +49,19 @@ struct Ctx {
 
 inline void rec(Ctx& c, int p, double cx, double cy, double h) {
     const BhHostTree& t = c.t;
-    const int d = t.lvl[p];
+    const int d = t.sk[p].level;
     if (c.leaf[p]) {
-        c.out.put(cx, cy, h, t.cmass[p], t.comx[p], t.comy[p], (int32_t)t.order[c.first[p]]);
+        c.out.put(cx, cy, h, t.cd[p].mass, t.cd[p].comx, t.cd[p].comy, (int32_t)t.order[c.first[p]]);
         return;
     }
-    c.out.put(cx, cy, h, t.cmass[p], t.comx[p], t.comy[p], -2);
+    c.out.put(cx, cy, h, t.cd[p].mass, t.cd[p].comx, t.cd[p].comy, -2);
     const double hh = h / 2.0;
     int ch = p + 1;
-    const int end = t.skip[p];
+    const int end = t.sk[p].skip;
     if (d >= t.root.levels) {
         // jitter-regime cluster (bodies sharing a cell with h < 1e-3): not a reference-shaped
         // subtree; list its bodies as leaves of child 0's geometry so the export stays total.
-        for (; ch < end; ch = t.skip[ch]) rec(c, ch, cx - hh, cy - hh, hh);
+        for (; ch < end; ch = t.sk[ch].skip) rec(c, ch, cx - hh, cy - hh, hh);
         return;
     }
     const int sh = 2 * (t.root.levels - 1 - d);
@@ -71,7 +70,7 @@ inline void rec(Ctx& c, int p, double cx, double cy, double h) {
         const double ccy = (dig & 2) ? cy + hh : cy - hh;
         if (ch < end && (int)((t.keys[c.first[ch]] >> sh) & 3ull) == dig) {
             rec(c, ch, ccx, ccy, hh);
-            ch = t.skip[ch];
+            ch = t.sk[ch].skip;
         } else {
             c.out.put(ccx, ccy, hh, 0.0, ccx, ccy, -1);      // empty leaf, BH.kt:179-183
         }

@@ -1,0 +1,294 @@
+#!/usr/bin/env python
+"""bench.py — the reference's headline metric on B200: body-interactions/s (and steps/s)
+of PhysicsEngine.step() (2 tree builds + 2 force evaluations + kick-drift-kick) at θ = 0.5.
+
+    python bench.py --gpus N --steps K --warmup W            # CUDA engine (the product)
+    python bench.py --impl reference --steps K --warmup W    # the reference CPU path (oracle port)
+    torchrun --nproc-per-node N ... bench.py --gpus N ...    # one rank per GPU
+
+A "step" is one PhysicsEngine.step() on the synthetic workload.  At N = 1 the workload is
+BASELINE.json configs[1]: the 1M-body uniform 'C' cloud (BodyFactory.makeUniformRandom
+semantics, m = 0.5, 2400x800 window, θ = 0.5, G = 80, Δt = 0.005, merge off).  For N > 1
+GPUs the cloud has 1M bodies PER GPU (window area scaled by N: constant density), the tree
+is replicated, every GPU walks and integrates its Morton slice, and the drifted positions
+are all-gathered over NCCL (weak scaling).  One JSON line is printed by rank 0.
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+BODIES_PER_GPU = 1_000_000
+THETA = 0.5
+
+
+def workload(n_gpus, bodies_per_gpu):
+    from bh_b200 import scenes
+    n = bodies_per_gpu * n_gpus
+    s = math.sqrt(n_gpus)
+    W, H = int(round(2400 * s)), int(round(800 * s))
+    return scenes.make_uniform_random(n, 0.5, W, H, seed=3), W, H
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows, self.proc, self.gpu = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[k] for r in self.rows if len(r) >= 9 for k in range(4) if r[5 + k].lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)), "MEASURED_PEAKS.json"
+        except Exception:
+            pass
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}, "fallback (B200_PROFILING.md)"
+
+
+def run_reference(args, rank, world):
+    """The reference's own CPU implementation of the path (JVM unavailable: the literal C++
+    port in oracle/) on all host threads, same config/metric as the CUDA arm."""
+    if rank != 0:
+        return
+    import bh_b200
+    lib = bh_b200.bind(os.path.join(ROOT, "oracle", "libbh_ref.so"))
+    scene, W, H = workload(max(1, args.gpus), args.bodies)
+    e = bh_b200.NativeEngine(lib=lib)
+    e.set_window(W, H)
+    e.set_params(theta=THETA, merge_min_dist=0.0)
+    e.set_bodies(*scene)
+    cores = lib.bh_ref_threads(e._h)
+    e.step(args.warmup)
+    e.reset_counters()
+    t0 = time.perf_counter()
+    e.step(args.steps)
+    dt = time.perf_counter() - t0
+    c = e.counters()
+    val = c["total_interactions"] / dt
+    out = {
+        "impl": "reference", "metric": "body_interactions_per_s", "value": val, "unit": "interactions/s",
+        "steps_per_s": args.steps / dt, "n_gpus": max(1, args.gpus), "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"{len(scene[0])}-body uniform 'C' cloud, theta={THETA}, {W}x{H} window, G=80, dt=0.005, merge off",
+                   "step": "PhysicsEngine.step(): 2 builds + 2 evaluations + KDK"},
+        "cpu_baseline": {"value": val, "unit": "interactions/s", "cores": int(cores), "kind": "port",
+                         "sample": f"{args.steps} full steps of the same workload (C++ port of BarnesHutAlg.kt; no JVM in the image)"},
+        "e2e": {"value": val, "unit": "interactions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "phases_ms_per_step": {"build": c["ms_build"] / args.steps, "walk": c["ms_walk"] / args.steps,
+                               "integrate": c["ms_integrate"] / args.steps},
+    }
+    print(json.dumps(out), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=None)
+    ap.add_argument("--warmup", type=int, default=None)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--bodies", type=int, default=BODIES_PER_GPU, help="bodies per GPU")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        args.steps = args.steps if args.steps is not None else 3
+        args.warmup = args.warmup if args.warmup is not None else 1
+        run_reference(args, rank, world)
+        return
+    args.steps = args.steps if args.steps is not None else 20
+    args.warmup = max(3, args.warmup if args.warmup is not None else 3)
+
+    import torch
+    import torch.distributed as dist
+    import bh_b200
+
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    n_gpus = world
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def allmax(v):
+        if world == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def allsum(v):
+        if world == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    scene, W, H = workload(n_gpus, args.bodies)
+    n = len(scene[0])
+    eng = bh_b200.NativeEngine(device=local_rank, capacity_hint=n)
+    eng.set_window(W, H)
+    eng.set_params(theta=THETA, merge_min_dist=0.0)
+    if world > 1:
+        uid = [eng.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        eng.comm_init(rank, world, uid[0])
+    eng.set_bodies(*scene)
+
+    # ---- device-resident throughput: K steps, inputs already in HBM ------------------------
+    eng.step(args.warmup)
+    eng.reset_counters()
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    t0 = time.perf_counter()
+    eng.step(args.steps)
+    barrier()
+    wall = time.perf_counter() - t0
+    clocks = sampler.stop()
+    c = eng.counters()
+    dev_ms = allmax(c["ms_step_call"])              # CUDA events on the engine's stream, max over ranks
+    wall = allmax(wall)
+    inter = allsum(float(c["total_interactions"]))
+    opened = allsum(float(c["total_opened"]))
+    launches = int(c["kernel_launches"])
+    value = inter / (dev_ms * 1e-3)
+    n_walks = 2 * args.steps
+    walk_ms = allmax(c["ms_walk"]) / n_walks
+    build_ms = allmax(c["ms_build"]) / n_walks
+
+    # ---- roofline of the dominant kernel (k_walk): FP32-issue bound -------------------------
+    peaks, peak_src = measured_peaks()
+    fp32 = np.zeros(1)
+    import ctypes as C
+    eng.lib.bh_measure_fp32_tflops(local_rank, fp32.ctypes.data_as(C.POINTER(C.c_double)))
+    my_inter, my_open = float(c["total_interactions"]) / n_walks, float(c["total_opened"]) / n_walks
+    walk_flops = 14.0 * my_inter + 8.0 * my_open           # 14 flop/interaction + 8 flop/rejected test
+    ach = walk_flops / (c["ms_walk"] / n_walks * 1e-3) / 1e12
+    roofline = {"kernel": "k_walk", "bound": "fp32", "achieved": ach, "peak": float(fp32[0]), "unit": "TFLOP/s",
+                "frac": ach / float(fp32[0]) if fp32[0] > 0 else None, "traffic": None,
+                "peak_source": "measured live: FFMA microbenchmark (bh_measure_fp32_tflops); the walk is FP32-issue/L1-latency bound, not HBM or tensor",
+                "ms_per_launch": c["ms_walk"] / n_walks,
+                "algorithmic": "14 flop x interactions + 8 flop x rejected opening tests per launch"}
+    # the HBM-bound phase: keygen + onesweep sort + scan + emit + climb (algorithmic bytes/body)
+    passes = (2 * c["key_levels"] + 1 + 7) // 8
+    cells_per_body = c["n_cells"] / max(1, c["n_in_tree"])
+    bytes_per_body = 24 + 8 + passes * 24 + 12 + cells_per_body * (13 + 73) + 24
+    bw = bytes_per_body * n / (build_ms * 1e-3) / 1e9
+    roofline_build = {"kernel": "build phase (k_keygen, k_histogram, k_onesweep_pass x%d, k_count_scan, k_emit, k_climb)" % passes,
+                      "bound": "hbm", "achieved": bw, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": bw / peaks["hbm_gbs"],
+                      "traffic": None, "peak_source": peak_src, "ms_per_build": build_ms,
+                      "algorithmic_bytes_per_body": bytes_per_body}
+
+    # ---- end to end through the C ABI with HOST buffers --------------------------------------
+    host = [torch.from_numpy(np.ascontiguousarray(a)).pin_memory() for a in scene]
+    hnp = [t.numpy() for t in host]
+    out = [torch.empty(n, dtype=torch.float64).pin_memory() for _ in range(5)]
+    onp = tuple(t.numpy() for t in out)
+    e2e_steps = max(3, min(args.steps, 10))
+    eng.set_bodies(*hnp); eng.step(1); eng.get_bodies(out=onp)
+    eng.reset_counters()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        eng.set_bodies(*hnp)            # H2D of this step's inputs (pinned host memory)
+        eng.step(1)
+        eng.get_bodies(out=onp)         # D2H of the step's result
+    barrier()
+    e2e_wall = allmax(time.perf_counter() - t0)
+    e2e_inter = allsum(float(eng.counters()["total_interactions"]))
+    e2e = {"value": e2e_inter / e2e_wall, "unit": "interactions/s", "steps_per_s": e2e_steps / e2e_wall,
+           "h2d_bytes_per_step": 5 * 8 * n, "d2h_bytes_per_step": 5 * 8 * n, "steps": e2e_steps,
+           "api": "bh_set_bodies + bh_step(1) + bh_get_bodies per step, pinned host arrays"}
+
+    # ---- CPU baseline beside it (rank 0, N = 1 only) ------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        lib = bh_b200.bind(os.path.join(ROOT, "oracle", "libbh_ref.so"))
+        o = bh_b200.NativeEngine(lib=lib)
+        o.set_window(W, H)
+        o.set_params(theta=THETA, merge_min_dist=0.0)
+        o.set_bodies(*scene)
+        o.reset_counters()
+        t0 = time.perf_counter()
+        o.step(2)
+        dt = time.perf_counter() - t0
+        oc = o.counters()
+        cpu = {"value": oc["total_interactions"] / dt, "unit": "interactions/s", "cores": int(lib.bh_ref_threads(o._h)),
+               "kind": "port", "steps_per_s": 2 / dt,
+               "sample": "2 full steps of the same 1M-body workload (C++ port of BarnesHutAlg.kt; the JVM reference cannot run in this image)"}
+        o.close()
+
+    if rank == 0:
+        line = {
+            "metric": "body_interactions_per_s", "value": value, "unit": "interactions/s",
+            "steps_per_s": args.steps / (dev_ms * 1e-3), "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": dev_ms / args.steps, "wall_ms_per_step": wall / args.steps * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32 interactions, f64 state/COM/integrator", "data": "synthetic",
+            "config": {"workload": f"{n}-body uniform 'C' cloud ({args.bodies}/GPU), theta={THETA}, {W}x{H} window, G=80, dt=0.005, merge off",
+                       "step": "PhysicsEngine.step(): 2 builds + 2 evaluations + KDK",
+                       "parallelism": "single GPU" if n_gpus == 1 else f"replicated tree, {n_gpus} Morton slices of targets, NCCL all-gather of positions",
+                       "l2": "no flush: per-step working set (~210 B/body state+sort+tree) exceeds the 126 MB L2 and is rewritten every build"},
+            "interactions_per_step": inter / args.steps, "opened_per_step": opened / args.steps,
+            "phases_ms_per_evaluation": {"build": build_ms, "walk": walk_ms},
+            "roofline": roofline, "roofline_build": roofline_build, "cpu_baseline": cpu, "e2e": e2e,
+            "gpu_launches": launches, "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

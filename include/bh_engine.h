@@ -97,6 +97,9 @@ typedef struct bh_counters {
     double  ms_integrate;
     double  ms_merge;
     double  ms_comm;
+    double  ms_step_call;       /* device time (CUDA events on the engine's stream) of */
+                                /*   the most recent bh_step call, all its steps       */
+    int64_t kernel_launches;    /* CUDA kernels launched since bh_reset_counters       */
 } bh_counters;
 
 /* ---- lifecycle ---------------------------------------------------------- */
@@ -185,6 +188,13 @@ int bh_comm_unique_id(void* id_out, int32_t id_bytes);
 int bh_comm_init(bh_engine* e, int32_t rank, int32_t world, const void* id, int32_t id_bytes);
 /* the slice [lo,hi) of home-ordered bodies rank `rank` of `world` owns */
 int bh_slice_bounds(int64_t n, int32_t world, int32_t rank, int64_t* lo, int64_t* hi);
+
+/* ---- diagnostics ---------------------------------------------------------- */
+
+/* Measured FP32 FMA throughput of `device` in TFLOP/s (2 flop per FFMA): the roofline
+ * denominator of the force walk and the direct sum, which are FP32-issue bound rather
+ * than HBM- or tensor-bound.  Runs a register-only FFMA microbenchmark kernel. */
+int bh_measure_fp32_tflops(int32_t device, double* tflops);
 
 #ifdef __cplusplus
 }

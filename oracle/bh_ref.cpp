@@ -485,8 +485,10 @@ int bh_get_positions_f32(bh_engine* e, int64_t cap, float* xy, float* m, int64_t
 
 int bh_step(bh_engine* e, int32_t nsteps) {
     if (!e || nsteps < 0) return fail(e, BH_E_ARG, "bh_step: bad arguments");
+    const double t0 = now_ms();
     try { for (int s = 0; s < nsteps; ++s) e->step(); }
     catch (const std::bad_alloc&) { return fail(e, BH_E_OOM, "bh_step: out of memory"); }
+    e->ctr.ms_step_call = now_ms() - t0;
     return BH_OK;
 }
 
@@ -626,6 +628,8 @@ int bh_slice_bounds(int64_t n, int32_t world, int32_t rank, int64_t* lo, int64_t
     *hi = std::min<int64_t>(n, per * (rank + 1));
     return BH_OK;
 }
+
+int bh_measure_fp32_tflops(int32_t, double*) { return BH_E_UNSUPPORTED; }
 
 // ---- oracle-only observers (not part of bh_engine.h) --------------------------------
 // For every body: depth of the leaf holding it in the tree of the LAST build (0 = root,

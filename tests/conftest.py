@@ -1,0 +1,123 @@
+"""Shared fixtures.  `-m "not gpu"` runs here on CPU (oracle known answers, algorithm-core
+emulation vs oracle, host logic, ABI symbol checks); `-m gpu` are the parity tests proper
+and call the CUDA engine through the C ABI on a B200."""
+import ctypes as C
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import bh_b200  # noqa: E402
+
+ORACLE_SO = os.path.join(ROOT, "oracle", "libbh_ref.so")
+EMUL_SO = os.path.join(ROOT, "tests", "emul", "libbh_emul.so")
+CSRC = os.path.join(ROOT, "barnes-hut-n-body_b200", "csrc")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (B200); run with -m gpu on the GPU box")
+
+
+def _newer(target, sources):
+    if not os.path.exists(target):
+        return False
+    t = os.path.getmtime(target)
+    return all(os.path.getmtime(s) <= t for s in sources if os.path.exists(s))
+
+
+def _build_oracle():
+    srcs = [os.path.join(ROOT, "oracle", "bh_ref.cpp"), os.path.join(ROOT, "include", "bh_engine.h")]
+    if not _newer(ORACLE_SO, srcs):
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "-s"])
+    return ORACLE_SO
+
+
+def _build_emul():
+    srcs = [os.path.join(ROOT, "tests", "emul", "bh_emul.cpp"), os.path.join(CSRC, "bh_core.h"), os.path.join(CSRC, "bh_export.h")]
+    if not _newer(EMUL_SO, srcs):
+        subprocess.check_call(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-fno-strict-aliasing", "-fPIC", "-shared", "-o", EMUL_SO,
+                               os.path.join(ROOT, "tests", "emul", "bh_emul.cpp")])
+    return EMUL_SO
+
+
+@pytest.fixture(scope="session")
+def oracle_lib():
+    """The oracle (literal C++ port of BarnesHutAlg.kt) bound to the shared ctypes ABI."""
+    return bh_b200.bind(_build_oracle())
+
+
+@pytest.fixture(scope="session")
+def emul_lib():
+    lib = C.CDLL(_build_emul())
+    return lib
+
+
+@pytest.fixture(scope="session")
+def cuda_lib():
+    """The product library; GPU tests fail (not skip) if it is missing."""
+    return bh_b200.load_cuda_library()
+
+
+def make_engine(lib, scene, width=2400, height=800, flags=0, **params):
+    e = bh_b200.NativeEngine(lib=lib, flags=flags)
+    e.set_window(width, height)
+    params.setdefault("merge_min_dist", 0.0)
+    e.set_params(**params)
+    e.set_bodies(*scene)
+    return e
+
+
+def leaf_paths(oracle_lib, engine):
+    n = engine.n
+    depth = np.empty(n, np.int32)
+    path = np.empty(n, np.uint64)
+    fn = oracle_lib.bh_ref_get_leaf_paths
+    fn.restype = C.c_int
+    fn.argtypes = [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_uint64)]
+    assert fn(engine._h, depth.ctypes.data_as(C.POINTER(C.c_int32)), path.ctypes.data_as(C.POINTER(C.c_uint64))) == 0
+    return depth, path
+
+
+def key_levels(root_half):
+    """first depth whose half-side is < 1e-3 (the jitter threshold, BarnesHutAlg.kt:146)"""
+    d, h = 0, float(root_half)
+    while not h < 1e-3 and d < 31:
+        h /= 2.0
+        d += 1
+    return d
+
+
+# ---- the acceleration-parity metric ------------------------------------------
+ACC_TOL = 1.0e-5       # north_star: "per-body acceleration within 1e-5 relative (FP32 vs f64)"
+ACC_FLOOR = 0.05       # relative to max(|a_i|, ACC_FLOOR * rms|a|): the relative error of a
+                       # body whose net force cancels to ~0 is unbounded in any FP32 scheme
+
+
+def acc_errors(ax, ay, gx, gy):
+    a = np.hypot(ax, ay)
+    err = np.hypot(gx - ax, gy - ay)
+    rms = float(np.sqrt(np.mean(a ** 2))) if len(a) else 0.0
+    tiny = 1e-300
+    rel = err / np.maximum(a, tiny)
+    relf = err / np.maximum(np.maximum(a, ACC_FLOOR * rms), tiny)
+    return {
+        "median": float(np.median(rel)) if len(a) else 0.0,
+        "p99": float(np.quantile(rel, 0.99)) if len(a) else 0.0,
+        "max_unfloored": float(rel.max()) if len(a) else 0.0,
+        "max_floored": float(relf.max()) if len(a) else 0.0,
+        "normwise": float(np.sqrt((err ** 2).sum() / max((a ** 2).sum(), tiny))),
+        "frac_above_tol_unfloored": float((rel > ACC_TOL).mean()) if len(a) else 0.0,
+    }
+
+
+def assert_acc_parity(ax, ay, gx, gy, what=""):
+    s = acc_errors(ax, ay, gx, gy)
+    assert s["max_floored"] <= ACC_TOL, (what, s)
+    assert s["normwise"] <= 1e-6, (what, s)
+    assert s["p99"] <= ACC_TOL, (what, s)
+    return s

@@ -15,17 +15,15 @@ struct Emul {
     BhRoot root{};
     int n = 0, n_in = 0, M = 0;
     std::vector<uint64_t> key_by_body, keys;
-    std::vector<int> order, S, skip, parent, cnt, arrived;
-    std::vector<signed char> lvl;
-    std::vector<BhCellA> A;
-    std::vector<BhCellB> B;
-    std::vector<double> comx, comy, cmass;
+    std::vector<int> order, S, arrived;
+    std::vector<BhCell> cell;
+    std::vector<BhCellD> cd;
+    std::vector<BhCellS> sk;
     BhTreeView view() {
         BhTreeView t{};
         t.keys = keys.data(); t.order = order.data(); t.S = S.data();
-        t.A = A.data(); t.B = B.data(); t.comx = comx.data(); t.comy = comy.data(); t.cmass = cmass.data();
-        t.skip = skip.data(); t.parent = parent.data(); t.cnt = cnt.data(); t.arrived = arrived.data();
-        t.lvl = lvl.data(); t.n_in = n_in; t.M = M;
+        t.cell = cell.data(); t.cd = cd.data(); t.sk = sk.data(); t.arrived = arrived.data();
+        t.n_in = n_in; t.M = M;
         return t;
     }
 };
@@ -51,9 +49,8 @@ static void build(Emul& e, int n, const double* x, const double* y, const double
         e.S[i + 1] = e.S[i] + (dnext > dprev ? dnext - dprev : 0);
     }
     e.M = e.n_in + e.S[e.n_in];
-    e.skip.assign(e.M, 0); e.parent.assign(e.M, 0); e.cnt.assign(e.M, 0); e.arrived.assign(e.M, 0);
-    e.lvl.assign(e.M, 0); e.A.resize(e.M); e.B.resize(e.M);
-    e.comx.assign(e.M, 0); e.comy.assign(e.M, 0); e.cmass.assign(e.M, 0);
+    e.arrived.assign(e.M, 0);
+    e.cell.assign(e.M, BhCell{}); e.cd.assign(e.M, BhCellD{}); e.sk.assign(e.M, BhCellS{});
     BhTreeView t = e.view();
     for (int i = 0; i < e.n_in; ++i) bh_emit_body(t, e.root.levels, i);
     for (int i = 0; i < e.n_in; ++i) { const int b = e.order[i]; bh_climb_body(t, e.root, i, x[b], y[b], m[b]); }
@@ -70,14 +67,12 @@ int bh_emul_accelerations(int n, const double* x, const double* y, const double*
     Emul e;
     build(e, n, x, y, m, rcx, rcy, rhalf);
     BhTreeView t = e.view();
-    BhWalkParams w;
-    w.theta2 = theta * theta; w.soft2 = soft2; w.half = rhalf;
-    w.th2f = (float)w.theta2; w.soft2f = (float)soft2;
+    const BhWalkParams w = bh_walk_params(theta, soft2, rhalf);
     int64_t tI = 0, tO = 0, tR = 0;
     for (int si = 0; si < n; ++si) {
         const int b = e.order[si];
         const int self = si < e.n_in ? e.S[si + 1] + si : -1;
-        BhWalkResult r = bh_walk_body(t, w, x[b], y[b], self);
+        BhWalkResult r = bh_walk_body<true>(t, w, x[b], y[b], self);
         if (ax) ax[b] = (m[b] == 0.0) ? NAN : G * (double)r.ax;
         if (ay) ay[b] = (m[b] == 0.0) ? NAN : G * (double)r.ay;
         if (cntI) cntI[b] = r.interactions;
@@ -88,7 +83,7 @@ int bh_emul_accelerations(int n, const double* x, const double* y, const double*
         if (key_out) key_out[b] = e.key_by_body[b];
         if (depth_out) depth_out[b] = -1;
     }
-    for (int i = 0; i < e.n_in; ++i) if (depth_out) depth_out[e.order[i]] = e.lvl[e.S[i + 1] + i];
+    for (int i = 0; i < e.n_in; ++i) if (depth_out) depth_out[e.order[i]] = e.sk[e.S[i + 1] + i].level;
     if (order_out) std::memcpy(order_out, e.order.data(), sizeof(int) * (size_t)n);
     if (stats) { stats[0] = e.n_in; stats[1] = e.M; stats[2] = e.S[e.n_in]; stats[3] = tI; stats[4] = tO; stats[5] = tR; }
     return 0;
@@ -100,8 +95,7 @@ int bh_emul_tree(int n, const double* x, const double* y, const double* m, doubl
                  double* comy, int32_t* body) {
     Emul e;
     build(e, n, x, y, m, rcx, rcy, rhalf);
-    BhHostTree t{e.root, e.n_in, e.M, e.keys.data(), e.order.data(), e.S.data(), e.skip.data(), e.lvl.data(),
-                 e.comx.data(), e.comy.data(), e.cmass.data()};
+    BhHostTree t{e.root, e.n_in, e.M, e.keys.data(), e.order.data(), e.S.data(), e.sk.data(), e.cd.data()};
     BhCellsOut out;
     out.cap = cap; out.cx = cx; out.cy = cy; out.h = h; out.mass = mass; out.comx = comx; out.comy = comy; out.body = body;
     bh_export_cells(t, out);
@@ -110,3 +104,36 @@ int bh_emul_tree(int n, const double* x, const double* y, const double* m, doubl
 }
 
 }  // extern "C"
+
+// ---- design probe (not a test): size of the union of the cells visited by each group of
+// `group` consecutive Morton-sorted bodies vs. the per-body visit counts.  Used to choose
+// between per-lane and warp-lockstep traversal.
+extern "C" int bh_emul_union_stats(int n, const double* x, const double* y, const double* m, double rcx, double rcy,
+                                   double rhalf, double theta, double soft2, int group, double* out /*[4]*/) {
+    Emul e;
+    build(e, n, x, y, m, rcx, rcy, rhalf);
+    BhTreeView t = e.view();
+    const double theta2 = theta * theta;
+    std::vector<int> stamp(e.M, -1);
+    double sumU = 0, sumMax = 0, sumMean = 0, sumUI = 0;
+    int groups = 0;
+    for (int g0 = 0; g0 + group <= e.n_in; g0 += group, ++groups) {
+        int U = 0, UI = 0, vmax = 0; double vsum = 0;
+        std::vector<int> istamp;  // interactions union
+        for (int si = g0; si < g0 + group; ++si) {
+            const int b = e.order[si];
+            int v = 0, p = 0;
+            while (p < e.M) {
+                ++v;
+                if (stamp[p] != groups) { stamp[p] = groups; ++U; }
+                const bool leafish = e.cell[p].s2 < 0;
+                bool acc = leafish || bh_exact_accept(e.cd[p].comx, e.cd[p].comy, x[b], y[b], soft2, theta2, rhalf, e.sk[p].level);
+                p = acc ? e.sk[p].skip : p + 1;
+            }
+            vmax = std::max(vmax, v); vsum += v;
+        }
+        sumU += U; sumMax += vmax; sumMean += vsum / group; (void)UI; (void)sumUI;
+    }
+    out[0] = sumU / groups; out[1] = sumMax / groups; out[2] = sumMean / groups; out[3] = groups;
+    return 0;
+}

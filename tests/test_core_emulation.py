@@ -1,0 +1,109 @@
+"""The engine's per-element algorithm core (csrc/bh_core.h: key descent, preorder layout
+formulas, galloping searches, bottom-up f64 COM, guarded FP32 opening test) executed
+serially on the CPU by tests/emul/ and compared with the oracle.  This covers the tree
+logic where no GPU exists; the kernels that run it in parallel are tested with -m gpu."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from bh_b200 import scenes
+from conftest import ACC_TOL, acc_errors, key_levels, leaf_paths, make_engine
+
+D = C.POINTER(C.c_double)
+I32 = C.POINTER(C.c_int32)
+I64 = C.POINTER(C.c_int64)
+U64 = C.POINTER(C.c_uint64)
+
+
+def _dp(a):
+    return a.ctypes.data_as(D)
+
+
+def emul_acc(emul, scene, p, theta):
+    x, y, vx, vy, m = (np.ascontiguousarray(a, np.float64) for a in scene)
+    n = len(x)
+    out = dict(ax=np.empty(n), ay=np.empty(n), ci=np.empty(n, np.int32), co=np.empty(n, np.int32),
+               key=np.empty(n, np.uint64), depth=np.empty(n, np.int32), order=np.empty(n, np.int32),
+               stats=np.zeros(6, np.int64))
+    emul.bh_emul_accelerations(n, _dp(x), _dp(y), _dp(m), C.c_double(p.root_cx), C.c_double(p.root_cy),
+                               C.c_double(p.root_half), C.c_double(theta), C.c_double(p.soft2), C.c_double(p.G),
+                               _dp(out["ax"]), _dp(out["ay"]), out["ci"].ctypes.data_as(I32), out["co"].ctypes.data_as(I32),
+                               out["key"].ctypes.data_as(U64), out["depth"].ctypes.data_as(I32),
+                               out["order"].ctypes.data_as(I32), out["stats"].ctypes.data_as(I64))
+    return out
+
+
+def emul_tree(emul, scene, p, k):
+    x, y, vx, vy, m = (np.ascontiguousarray(a, np.float64) for a in scene)
+    t = {q: np.empty(k) for q in ("cx", "cy", "h", "mass", "comx", "comy")}
+    body = np.empty(k, np.int32)
+    nc = C.c_int64()
+    emul.bh_emul_tree(len(x), _dp(x), _dp(y), _dp(m), C.c_double(p.root_cx), C.c_double(p.root_cy), C.c_double(p.root_half),
+                      C.c_int64(k), C.byref(nc), _dp(t["cx"]), _dp(t["cy"]), _dp(t["h"]), _dp(t["mass"]), _dp(t["comx"]),
+                      _dp(t["comy"]), body.ctypes.data_as(I32))
+    t["body"] = body
+    return nc.value, t
+
+
+def _oob_scene():
+    s = scenes.make_uniform_random(3000, 0.5, seed=5)
+    s[0][:50] += 3000.0            # 50 bodies outside the root box
+    s[4][100:120] = 0.0            # zero-mass bodies
+    return s
+
+
+CASES = [
+    ("two-disk θ0.5", lambda: scenes.snap_f32(scenes.default_two_disks()), 2400, 800, 0.5),
+    ("two-disk θ0.3", lambda: scenes.snap_f32(scenes.default_two_disks(seed=11)), 2400, 800, 0.3),
+    ("uniform 20k unsnapped θ1.6", lambda: scenes.make_uniform_random(20000, 0.5), 2400, 800, 1.6),
+    ("uniform 20k θ0.2", lambda: scenes.make_uniform_random(20000, 0.5, seed=4), 2400, 800, 0.2),
+    ("out-of-box + zero mass", _oob_scene, 2400, 800, 1.0),
+    ("big box", lambda: scenes.default_two_disks(32768, 32768, 8000, 2000, scale=28.0, seed=4), 32768, 32768, 0.5),
+    ("n=2", lambda: scenes.make_uniform_random(2, 0.5), 2400, 800, 0.5),
+    ("n=1", lambda: scenes.make_uniform_random(1, 0.5), 2400, 800, 0.5),
+    ("theta=0", lambda: scenes.make_uniform_random(300, 0.5, seed=8), 2400, 800, 0.0),
+]
+
+
+@pytest.mark.parametrize("name,gen,W,H,theta", CASES, ids=[c[0] for c in CASES])
+def test_core_matches_oracle(oracle_lib, emul_lib, name, gen, W, H, theta):
+    scene = gen()
+    n = len(scene[0])
+    o = make_engine(oracle_lib, scene, W, H, flags=1, theta=theta)
+    p = o.params
+    ax, ay = o.compute_accelerations()
+    ci, co = o.body_counts()
+    depth, path = leaf_paths(oracle_lib, o)
+    g = emul_acc(emul_lib, scene, p, theta)
+    # Morton order and cell assignment: bit-exact
+    L = key_levels(p.root_half)
+    assert (g["depth"] == depth).all()
+    inb = depth >= 0
+    assert ((g["key"][inb] >> (2 * (L - depth[inb])).astype(np.uint64)) == path[inb]).all()
+    assert (g["key"][~inb] == np.uint64(0xFFFFFFFFFFFFFFFF)).all()
+    # per-body decisions identical: interaction and opened-cell counts are integers
+    assert (g["ci"] == ci).all() and (g["co"] == co).all()
+    # accelerations (host FP32 arithmetic here; the device numbers are gated in test_gpu_parity)
+    ok = np.isfinite(ax)
+    assert (np.isnan(g["ax"]) == ~ok).all()
+    if ok.sum() > 2:
+        s = acc_errors(ax[ok], ay[ok], g["ax"][ok], g["ay"][ok])
+        assert s["normwise"] < 1e-6 and s["max_floored"] < 2 * ACC_TOL, s
+    # every cell of visitQuads, bit-exact incl. the f64 centres of mass
+    to = o.tree()
+    k, tg = emul_tree(emul_lib, scene, p, len(to["cx"]))
+    assert k == len(to["cx"])
+    for q in to:
+        assert (tg[q] == to[q]).all(), q
+
+
+def test_insertion_order_invariance(oracle_lib):
+    """Outside the jitter regime the reference tree does not depend on insertion order
+    (BH.kt:125-137), which is what lets a sort-based build reproduce it."""
+    s = scenes.make_uniform_random(5000, 0.5, seed=2)
+    perm = np.random.default_rng(0).permutation(5000)
+    a = make_engine(oracle_lib, s).tree()
+    b = make_engine(oracle_lib, tuple(v[perm] for v in s)).tree()
+    for q in ("cx", "cy", "h", "mass"):
+        assert (a[q] == b[q]).all()

@@ -1,0 +1,236 @@
+"""GPU parity: the CUDA engine (through the C ABI) against the oracle on identical inputs.
+
+Gates (BASELINE.json north_star):
+  * Morton order and cell assignment: bit-exact (keys, leaf depths, sort order, every cell
+    of visitQuads incl. the f64 centres of mass);
+  * per-body accept/open decisions: interaction and opened-cell counts equal as integers;
+  * per-body acceleration: |da| <= 1e-5 * max(|a_i|, 0.05 rms|a|), p99 of the unfloored
+    relative error <= 1e-5, norm-wise error <= 1e-6   (conftest.assert_acc_parity);
+  * trajectories: 10 steps within 1e-5 relative; 1000-step energy drift bounded by the
+    oracle's own drift."""
+import math
+
+import numpy as np
+import pytest
+
+from bh_b200 import scenes
+from conftest import ACC_TOL, acc_errors, assert_acc_parity, key_levels, leaf_paths, make_engine
+
+pytestmark = pytest.mark.gpu
+
+
+def _oob_scene():
+    s = scenes.make_uniform_random(3000, 0.5, seed=5)
+    s[0][:50] += 3000.0
+    s[1][50:60] -= 5000.0
+    return s
+
+
+CASES = [
+    ("C1 two-disk 12.5k θ0.5", lambda: scenes.snap_f32(scenes.default_two_disks()), 2400, 800, 0.5),
+    ("C1 two-disk 12.5k θ0.30 (code default)", lambda: scenes.snap_f32(scenes.default_two_disks(seed=2)), 2400, 800, 0.30),
+    ("two-disk 2x10k θ0.5", lambda: scenes.snap_f32(scenes.default_two_disks(n1=10000, n2=10000, seed=3)), 2400, 800, 0.5),
+    ("uniform 20k unsnapped θ0.2", lambda: scenes.make_uniform_random(20000, 0.5, seed=4), 2400, 800, 0.2),
+    ("uniform 20k θ1.6", lambda: scenes.make_uniform_random(20000, 0.5, seed=5), 2400, 800, 1.6),
+    ("out-of-box targets", _oob_scene, 2400, 800, 1.0),
+    ("big box 32768²", lambda: scenes.default_two_disks(32768, 32768, 40000, 10000, scale=2.0 * math.sqrt(5.0), seed=4), 32768, 32768, 0.5),
+    ("mixed-mass 131072²", lambda: scenes.mixed_mass_stress(8, 4000, 16, 131072, 131072, seed=8), 131072, 131072, 0.5),
+    ("uniform 200k θ0.5", lambda: scenes.make_uniform_random(200000, 0.5, seed=9), 2400, 800, 0.5),
+]
+
+
+@pytest.mark.parametrize("name,gen,W,H,theta", CASES, ids=[c[0] for c in CASES])
+def test_tree_decisions_and_accelerations_match_oracle(oracle_lib, cuda_lib, name, gen, W, H, theta):
+    scene = gen()
+    o = make_engine(oracle_lib, scene, W, H, flags=1, theta=theta)
+    g = make_engine(cuda_lib, scene, W, H, flags=1, theta=theta)
+    ax, ay = o.compute_accelerations()
+    gx, gy = g.compute_accelerations()
+    oc, gc = o.counters(), g.counters()
+    assert gc["n_jitter_bodies"] == 0, "parity inputs must stay out of the jitter regime"
+    # decisions
+    assert (oc["interactions"], oc["opened"]) == (gc["interactions"], gc["opened"])
+    oi, oo = o.body_counts()
+    gi, go = g.body_counts()
+    assert (oi == gi).all() and (oo == go).all()
+    # Morton order / cell assignment
+    depth, path = leaf_paths(oracle_lib, o)
+    key, gdepth, order = g.morton()
+    L = key_levels(g.params.root_half)
+    assert gc["key_levels"] == L
+    assert (gdepth == depth).all()
+    inb = depth >= 0
+    assert ((key[inb] >> (2 * (L - depth[inb])).astype(np.uint64)) == path[inb]).all()
+    assert (key[~inb] == np.uint64(0xFFFFFFFFFFFFFFFF)).all()
+    assert (order == np.argsort(key, kind="stable")).all()          # sort: stable, exact
+    assert gc["n_in_tree"] == int(inb.sum()) and gc["n_out_of_box"] == int((~inb).sum())
+    # every cell, bit-exact
+    to, tg = o.tree(), g.tree()
+    assert len(to["cx"]) == len(tg["cx"])
+    for k in to:
+        assert (to[k] == tg[k]).all(), k
+    # accelerations
+    s = assert_acc_parity(ax, ay, gx, gy, name)
+    print(name, s)
+
+
+def test_full_size_1m_cloud(oracle_lib, cuda_lib):
+    """BASELINE config[1] at full size: 1M-body uniform cloud, θ = 0.5, vs the oracle."""
+    scene = scenes.make_uniform_random(1_000_000, 0.5, seed=3)
+    o = make_engine(oracle_lib, scene, theta=0.5)
+    g = make_engine(cuda_lib, scene, flags=1, theta=0.5)
+    ax, ay = o.compute_accelerations()
+    gx, gy = g.compute_accelerations()
+    oc, gc = o.counters(), g.counters()
+    assert (oc["interactions"], oc["opened"]) == (gc["interactions"], gc["opened"])
+    s = assert_acc_parity(ax, ay, gx, gy, "1M cloud")
+    print("1M cloud", s, "retests", gc["exact_retests"])
+    # size-independent properties: the sort is a sorted permutation, the scan closes the tree
+    key, depth, order = g.morton()
+    assert (np.sort(order) == np.arange(len(order))).all()
+    assert (np.diff(key[order].astype(np.uint64)) >= 0).all() if False else (key[order][1:] >= key[order][:-1]).all()
+    assert gc["n_cells"] == gc["n_in_tree"] + gc["n_internal"]
+    gi, go = g.body_counts()
+    assert int(gi.sum()) == gc["interactions"] and int(go.sum()) == gc["opened"]
+
+
+def test_theta_sweep_error_vs_device_direct_sum(cuda_lib):
+    """C2: BH force error against the on-device all-pairs kernel grows monotonically with θ
+    over the reference's adjustable range 0.2-1.6 (NBodyPanel.kt:247-248)."""
+    scene = scenes.make_uniform_random(100_000, 0.5, seed=3)
+    g = make_engine(cuda_lib, scene)
+    dx, dy = g.direct_sum()
+    errs = []
+    for theta in (0.2, 0.3, 0.5, 0.8, 1.0, 1.3, 1.6):
+        g.set_params(theta=theta)
+        bx, by = g.compute_accelerations()
+        s = acc_errors(dx, dy, bx, by)
+        errs.append(s["normwise"])
+        print("theta", theta, "normwise", s["normwise"], "median", s["median"], "interactions/body", g.counters()["interactions"] / g.n)
+    assert all(a < b for a, b in zip(errs, errs[1:])), errs
+    assert errs[0] < 5e-3 and errs[2] < 5e-2
+
+
+def test_theta_zero_equals_direct_sum(oracle_lib, cuda_lib):
+    """θ = 0: s² < 0 never holds, every cell is opened, BH == direct sum."""
+    scene = scenes.snap_f32(scenes.make_uniform_random(2000, 0.5, seed=12))
+    g = make_engine(cuda_lib, scene, flags=1, theta=0.0)
+    bx, by = g.compute_accelerations()
+    gi, _ = g.body_counts()
+    assert (gi == 1999).all()
+    dx, dy = g.direct_sum()
+    o = make_engine(oracle_lib, scene, theta=0.0)
+    ox, oy = o.direct_sum()
+    assert_acc_parity(ox, oy, dx, dy, "device direct sum vs f64 direct sum")
+    assert_acc_parity(ox, oy, bx, by, "θ=0 walk vs f64 direct sum")
+
+
+def test_trajectory_10_steps(oracle_lib, cuda_lib):
+    scene = scenes.snap_f32(scenes.default_two_disks())
+    o = make_engine(oracle_lib, scene, theta=0.5)
+    g = make_engine(cuda_lib, scene, theta=0.5)
+    o.step(10)
+    g.step(10)
+    so, sg = o.get_bodies(), g.get_bodies()
+    pos_err = np.hypot(so[0] - sg[0], so[1] - sg[1]).max()
+    vel_err = np.hypot(so[2] - sg[2], so[3] - sg[3])
+    v = np.hypot(so[2], so[3])
+    assert pos_err <= 1e-5 * 2400 * 1e-2, pos_err                    # 1e-7 of the box
+    assert (vel_err / np.maximum(v, 0.05 * np.sqrt(np.mean(v ** 2)))).max() <= 1e-5
+    assert (so[4] == sg[4]).all()
+
+
+def test_energy_drift_1000_steps(oracle_lib, cuda_lib):
+    """H9 protocol: stable setting (Δt = 0.001, merge off, θ = 0.5), 1000 steps;
+    |ΔE/E0| on the GPU <= max(2 x the oracle's own BH drift, 1e-4)."""
+    scene = scenes.snap_f32(scenes.default_two_disks(n1=2400, n2=600, seed=31))
+    o = make_engine(oracle_lib, scene, theta=0.5, dt=0.001)
+    g = make_engine(cuda_lib, scene, theta=0.5, dt=0.001)
+    e0o, e0g = o.energy()["total"], g.energy()["total"]
+    assert abs(e0o - e0g) <= 1e-9 * abs(e0o)
+    o.step(1000)
+    g.step(1000)
+    do = abs(o.energy()["total"] - e0o) / abs(e0o)
+    dg = abs(g.energy()["total"] - e0g) / abs(e0g)
+    print("energy drift oracle", do, "gpu", dg)
+    assert dg <= max(2.0 * do, 1e-4)
+    # momentum is conserved by the symmetric scheme to rounding (merge off)
+    assert abs(g.energy()["px"] - o.energy()["px"]) <= 1e-6 * max(1.0, abs(o.energy()["px"]))
+
+
+def test_edge_cases(oracle_lib, cuda_lib):
+    z = np.zeros(0)
+    g = make_engine(cuda_lib, (z, z, z, z, z))
+    g.step(2)                                                   # resetBodies(emptyList), NBodyPanel.kt:144
+    assert g.n == 0 and len(g.tree()["cx"]) == 1 and g.tree()["body"][0] == -1
+    one = (np.array([10.0]), np.array([10.0]), np.array([1.0]), np.array([2.0]), np.array([7.0]))
+    g.set_bodies(*one)
+    ax, ay = g.compute_accelerations()
+    assert ax[0] == 0.0 and ay[0] == 0.0
+    g.step(1)
+    x, y, vx, vy, m = g.get_bodies()
+    assert (x[0], y[0], vx[0], vy[0]) == (10 + 1 * 0.005, 10 + 2 * 0.005, 1.0, 2.0)
+    # every body outside the root box: nobody is a source, everybody is integrated
+    far = (np.array([5000.0, 6000.0]), np.array([0.0, 0.0]), np.array([1.0, 0.0]), np.array([0.0, 1.0]), np.array([1.0, 1.0]))
+    g.set_bodies(*far)
+    ax, ay = g.compute_accelerations()
+    assert (ax == 0).all() and (ay == 0).all() and g.counters()["n_out_of_box"] == 2
+    # zero-mass target -> NaN like 0/0 in BH.kt:390-391; zero-mass source pruned (BH.kt:216)
+    b = np.array([[100, 100, 0, 0, 0.0], [200, 100, 0, 0, 2.0], [300, 300, 0, 0, 1.0]], float)
+    sc = tuple(b[:, k].copy() for k in range(5))
+    g2 = make_engine(cuda_lib, sc, flags=1, theta=0.5)
+    o2 = make_engine(oracle_lib, sc, flags=1, theta=0.5)
+    gx, gy = g2.compute_accelerations()
+    ox, oy = o2.compute_accelerations()
+    assert math.isnan(gx[0]) and math.isnan(gy[0])
+    assert (g2.body_counts()[0] == o2.body_counts()[0]).all()
+    assert np.allclose(gx[1:], ox[1:], rtol=1e-6) and np.allclose(gy[1:], oy[1:], rtol=1e-6)
+    # NaN position: fails contains() like any comparison with NaN (BH.kt:61-62)
+    b[0] = [float("nan"), 5.0, 0, 0, 1.0]
+    g3 = make_engine(cuda_lib, tuple(b[:, k].copy() for k in range(5)))
+    g3.compute_accelerations()
+    assert g3.counters()["n_out_of_box"] == 1
+    # coincident bodies (jitter regime): detected and reported, no crash, finite forces
+    s = scenes.make_uniform_random(1000, 0.5, seed=1)
+    s[0][1], s[1][1] = s[0][0], s[1][0]
+    g4 = make_engine(cuda_lib, s)
+    ax, ay = g4.compute_accelerations()
+    assert g4.counters()["n_jitter_bodies"] == 2 and np.isfinite(ax).all()
+
+
+def test_params_are_reread_every_call(oracle_lib, cuda_lib):
+    """Z/X, O/P, K/L keys change Config between steps (NBodyPanel.kt:247-260)."""
+    scene = scenes.snap_f32(scenes.default_two_disks(n1=1500, n2=500, seed=6))
+    o = make_engine(oracle_lib, scene, flags=1)
+    g = make_engine(cuda_lib, scene, flags=1)
+    for theta, G, dt in ((0.2, 80.0, 0.005), (1.6, 100.0, -0.003), (0.75, 0.0, 0.01)):
+        for e in (o, g):
+            e.set_params(theta=theta, G=G, dt=dt)
+            e.step(1)
+            e.compute_accelerations()
+        assert (o.body_counts()[0] == g.body_counts()[0]).all()
+    so, sg = o.get_bodies(), g.get_bodies()
+    assert np.hypot(so[0] - sg[0], so[1] - sg[1]).max() < 1e-6
+
+
+def test_kotlin_facade_drives_the_engine(cuda_lib):
+    """PhysicsEngine / Body / Config with the reference's names (NBodyPanel.kt call sites)."""
+    import bh_b200
+    from bh_b200 import Body, Config, PhysicsEngine
+    Config.reset()
+    Config.theta = 0.5
+    sc = scenes.default_two_disks(n1=600, n2=200, seed=5)
+    bodies = [Body(*[float(v[i]) for v in sc]) for i in range(len(sc[0]))]
+    eng = PhysicsEngine(bodies)
+    eng.mergeMinDist = 0.0
+    first = bodies[0]
+    x0 = first.x
+    eng.step()
+    assert eng.getBodies() is bodies and bodies[0] is first and first.x != x0 or first.vx == 0
+    quads = []
+    eng.getTreeForDebug().visitQuads(lambda q: quads.append(q))
+    assert quads[0] == bh_b200.Quad(1200.0, 400.0, 1202.0) and len(quads) > len(bodies)
+    eng.resetBodies([])
+    eng.step()
+    assert eng.getBodies() == []
+    Config.reset()
