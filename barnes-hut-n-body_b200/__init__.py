@@ -6,7 +6,9 @@ from ._abi import (BH_FLAG_BODY_COUNTS, BhConfig, BhCounters, BhError, BhParams,
                    CUDA_LIB_PATH, bind, load_cuda_library)
 from .engine import BHTree, Body, Config, NativeEngine, PhysicsEngine, Quad
 from . import scenes
+from . import distributed
+from ._abi import BH_FIELD_POS, BH_FIELD_VEL
 
 __all__ = ["BH_FLAG_BODY_COUNTS", "BhConfig", "BhCounters", "BhError", "BhParams", "CudaLibraryMissing",
            "CUDA_LIB_PATH", "bind", "load_cuda_library", "BHTree", "Body", "Config", "NativeEngine",
-           "PhysicsEngine", "Quad", "scenes"]
+           "PhysicsEngine", "Quad", "scenes", "distributed", "BH_FIELD_POS", "BH_FIELD_VEL"]

@@ -26,11 +26,14 @@ _ERR_NAMES = {
 
 BH_FLAG_BODY_COUNTS = 1
 BH_COMM_ID_BYTES = 128
+BH_FIELD_POS = 0
+BH_FIELD_VEL = 1
 
 
 class BhConfig(C.Structure):
     _fields_ = [("struct_size", C.c_int32), ("device", C.c_int32), ("threads", C.c_int32),
-                ("flags", C.c_uint32), ("capacity_hint", C.c_int64)]
+                ("flags", C.c_uint32), ("capacity_hint", C.c_int64),
+                ("rehome_interval", C.c_int32), ("reserved", C.c_int32)]
 
 
 class BhParams(C.Structure):
@@ -87,7 +90,13 @@ SYMBOLS = {
     "bh_get_body_counts": (C.c_int, [_H, _I32, _I32]),
     "bh_comm_unique_id": (C.c_int, [C.c_void_p, C.c_int32]),
     "bh_comm_init": (C.c_int, [_H, C.c_int32, C.c_int32, C.c_void_p, C.c_int32]),
+    "bh_comm_init_external": (C.c_int, [_H, C.c_int32, C.c_int32]),
     "bh_slice_bounds": (C.c_int, [C.c_int64, C.c_int32, C.c_int32, _I64, _I64]),
+    "bh_step_begin": (C.c_int, [_H]),
+    "bh_step_end": (C.c_int, [_H]),
+    "bh_step_finish": (C.c_int, [_H]),
+    "bh_export_slice": (C.c_int, [_H, C.c_int32, C.c_int64, _D, _D, _I64, _I64]),
+    "bh_import_slices": (C.c_int, [_H, C.c_int32, C.c_int64, _D, _D]),
     "bh_measure_fp32_tflops": (C.c_int, [C.c_int32, _D]),
 }
 

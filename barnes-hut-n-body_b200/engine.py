@@ -40,9 +40,9 @@ class NativeEngine:
     """One ``bh_engine*``.  `lib` defaults to the CUDA product library (no CPU fallback)."""
 
     def __init__(self, lib: Optional[C.CDLL] = None, device: int = 0, threads: int = 0,
-                 flags: int = 0, capacity_hint: int = 0):
+                 flags: int = 0, capacity_hint: int = 0, rehome_interval: int = 0):
         self.lib = lib if lib is not None else _abi.load_cuda_library()
-        cfg = BhConfig(C.sizeof(BhConfig), device, threads, flags, capacity_hint)
+        cfg = BhConfig(C.sizeof(BhConfig), device, threads, flags, capacity_hint, rehome_interval, 0)
         h = C.c_void_p()
         rc = self.lib.bh_create(C.byref(cfg), C.byref(h))
         if rc != _abi.BH_OK:
@@ -205,6 +205,32 @@ class NativeEngine:
     def comm_init(self, rank: int, world: int, unique_id: bytes):
         buf = C.create_string_buffer(unique_id, _abi.BH_COMM_ID_BYTES)
         self._check(self.lib.bh_comm_init(self._h, rank, world, buf, _abi.BH_COMM_ID_BYTES), "bh_comm_init")
+
+    def comm_init_external(self, rank: int, world: int):
+        """Host-staged transport: the caller exchanges slices (see :mod:`.distributed`)."""
+        self._check(self.lib.bh_comm_init_external(self._h, rank, world), "bh_comm_init_external")
+
+    def step_begin(self):
+        self._check(self.lib.bh_step_begin(self._h), "bh_step_begin")
+
+    def step_end(self):
+        self._check(self.lib.bh_step_end(self._h), "bh_step_end")
+
+    def step_finish(self):
+        self._check(self.lib.bh_step_finish(self._h), "bh_step_finish")
+
+    def export_slice(self, field: int):
+        """(a, b, lo, hi): this rank's slice of (x, y) or (vx, vy) in the engine's home order."""
+        n = self.n
+        lo, hi = C.c_int64(), C.c_int64()
+        a, b = np.empty(n, np.float64), np.empty(n, np.float64)
+        self._check(self.lib.bh_export_slice(self._h, field, n, _dp(a), _dp(b), C.byref(lo), C.byref(hi)), "bh_export_slice")
+        k = hi.value - lo.value
+        return a[:k], b[:k], lo.value, hi.value
+
+    def import_slices(self, field: int, a, b):
+        a, b = _f64(a), _f64(b)
+        self._check(self.lib.bh_import_slices(self._h, field, a.shape[0], _dp(a), _dp(b)), "bh_import_slices")
 
     def slice_bounds(self, n: int, world: int, rank: int):
         lo, hi = C.c_int64(), C.c_int64()

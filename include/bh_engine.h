@@ -54,6 +54,9 @@ typedef struct bh_config {
     int32_t  threads;       /* oracle: worker threads, 0 = all cores (:292,:377)   */
     uint32_t flags;         /* BH_FLAG_*                                           */
     int64_t  capacity_hint; /* bodies to pre-size buffers for (0 = grow on demand) */
+    int32_t  rehome_interval; /* CUDA engine: re-sort the device-resident state into Morton
+                               * ("home") order every this many steps; 0 = default (8)      */
+    int32_t  reserved;
 } bh_config;
 
 /* The values the reference reads live from `object Config` on every use
@@ -177,17 +180,46 @@ int bh_reset_counters(bh_engine* e);
 /* per-body counts of the last evaluation (needs BH_FLAG_BODY_COUNTS) */
 int bh_get_body_counts(bh_engine* e, int32_t* interactions, int32_t* opened);
 
-/* ---- multi-GPU: replicated tree, Morton-sliced targets (no reference
- *      counterpart; the reference is single-process) ------------------------ */
+/* ---- multi-GPU / multi-process: replicated tree, Morton-sliced targets (no reference
+ *      counterpart; the reference is single-process).
+ *
+ * Every rank holds the full body list (same bh_set_bodies on every rank) and builds the full
+ * tree; rank r walks and integrates only its slice [lo,hi) of the engine's internal ("home",
+ * Morton-sorted at the last re-homing) body order, which is identical on every rank.  One
+ * exchange of the drifted positions per step.  Results are bit-identical to one process.
+ * Two transports:
+ *   bh_comm_init           NCCL inside the engine (CUDA library only): bh_step() is complete.
+ *   bh_comm_init_external  host-staged: the caller moves the slices between ranks with its own
+ *                          transport (MPI, gloo, JVM sockets ...) and drives a step as
+ *                              bh_step_begin            a(t), half kick, drift   (own slice)
+ *                              exchange BH_FIELD_POS    bh_export_slice -> all-gather -> bh_import_slices
+ *                              bh_step_end              a(t+dt), half kick       (own slice)
+ *                              exchange BH_FIELD_VEL
+ *                              bh_step_finish           merge rule, counters
+ * ------------------------------------------------------------------------------------------ */
 
 #define BH_COMM_ID_BYTES 128
-/* rank 0 creates an id and ships it to the other ranks (torch.distributed, a file…) */
+#define BH_FIELD_POS 0   /* (x, y)   */
+#define BH_FIELD_VEL 1   /* (vx, vy) */
+/* rank 0 creates an id and ships it to the other ranks (torch.distributed, a file...) */
 int bh_comm_unique_id(void* id_out, int32_t id_bytes);
-/* every rank: join a `world`-rank communicator; afterwards bh_step walks only this
- * rank's slice of targets and all-gathers the drifted positions over NCCL. */
+/* every rank: join a `world`-rank NCCL communicator; afterwards bh_step walks only this
+ * rank's slice of targets and all-gathers the drifted positions over NCCL / NVLink. */
 int bh_comm_init(bh_engine* e, int32_t rank, int32_t world, const void* id, int32_t id_bytes);
+/* every rank: host-staged transport (see above); bh_step() is then refused for world > 1. */
+int bh_comm_init_external(bh_engine* e, int32_t rank, int32_t world);
 /* the slice [lo,hi) of home-ordered bodies rank `rank` of `world` owns */
 int bh_slice_bounds(int64_t n, int32_t world, int32_t rank, int64_t* lo, int64_t* hi);
+/* the three phases of PhysicsEngine.step() (BarnesHutAlg.kt:405-439) for the host-staged
+ * transport; with world == 1 their sequence equals bh_step(e, 1). */
+int bh_step_begin(bh_engine* e);    /* :407-422  build, a(t), v += a dt/2, x += v dt */
+int bh_step_end(bh_engine* e);      /* :425-435  build, a(t+dt), v += a dt/2         */
+int bh_step_finish(bh_engine* e);   /* :438      mergeCloseBodiesIfNeeded()          */
+/* this rank's slice of `field` in home order: a[0..hi-lo), b[0..hi-lo); cap >= hi-lo */
+int bh_export_slice(bh_engine* e, int32_t field, int64_t cap, double* a, double* b,
+                    int64_t* lo, int64_t* hi);
+/* the concatenation of every rank's exported slice (n = bh_num_bodies doubles each) */
+int bh_import_slices(bh_engine* e, int32_t field, int64_t n, const double* a, const double* b);
 
 /* ---- diagnostics ---------------------------------------------------------- */
 

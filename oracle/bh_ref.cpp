@@ -216,6 +216,10 @@ struct bh_engine {
     std::vector<int32_t> origin;   // observer: index at bh_set_bodies time of each surviving body
     bh_counters ctr{};
     std::string err;
+    // host-staged multi-process protocol of include/bh_engine.h (no reference counterpart): this
+    // rank evaluates and integrates only the list positions [lo, hi) of bh_slice_bounds
+    int rank = 0, world = 1, phase = 0;
+    void mySlice(int64_t* lo, int64_t* hi) const { bh_slice_bounds((int64_t)bodies.size(), world, rank, lo, hi); }
 
     // BH.kt:359-366
     BHTree* buildTree() {
@@ -230,15 +234,15 @@ struct bh_engine {
     }
 
     // BH.kt:374-395 — min(cores, n) workers pulling indices from one atomic counter
-    void computeAccelerations(const BHTree* root) {
+    void computeAccelerations(const BHTree* root, int64_t first = 0, int64_t last = -1) {
         const double t0 = now_ms();
-        const int64_t n = (int64_t)bodies.size();
+        const int64_t n = last < 0 ? (int64_t)bodies.size() : last;
         const int workers = (int)std::min<int64_t>(cores, std::max<int64_t>(n, 1));
         const double theta2 = par.theta * par.theta;
         const Params P{par.G, par.soft2};
         const bool keep = (cfg.flags & BH_FLAG_BODY_COUNTS) != 0;
-        if (keep) { cntI.assign(n, 0); cntO.assign(n, 0); }
-        std::atomic<int64_t> next{0};
+        if (keep) { cntI.assign(bodies.size(), 0); cntO.assign(bodies.size(), 0); }
+        std::atomic<int64_t> next{first};
         std::atomic<int64_t> totI{0}, totO{0};
         auto work = [&]() {
             Acc acc;
@@ -271,28 +275,40 @@ struct bh_engine {
         ctr.ms_walk += now_ms() - t0;
     }
 
-    // BH.kt:405-439
-    void step() {
+    // BH.kt:405-439, in the three phases of the ABI (world == 1: the slice is the whole list)
+    void stepBegin() {   // :407-422
+        int64_t lo, hi;
+        mySlice(&lo, &hi);
         BHTree* root = buildTree();
-        computeAccelerations(root);
-        double t0 = now_ms();
+        computeAccelerations(root, lo, hi);
+        const double t0 = now_ms();
         const double dt = par.dt;
         const double dtHalf = dt * 0.5;
-        const size_t n = bodies.size();
-        for (size_t i = 0; i < n; ++i) { bodies[i].vx += ax[i] * dtHalf; bodies[i].vy += ay[i] * dtHalf; }
-        for (auto& b : bodies) { b.x += b.vx * dt; b.y += b.vy * dt; }
+        for (int64_t i = lo; i < hi; ++i) { bodies[i].vx += ax[i] * dtHalf; bodies[i].vy += ay[i] * dtHalf; }
+        for (int64_t i = lo; i < hi; ++i) { Body& b = bodies[i]; b.x += b.vx * dt; b.y += b.vy * dt; }
         ctr.ms_integrate += now_ms() - t0;
-        root = buildTree();
-        computeAccelerations(root);
-        t0 = now_ms();
-        for (size_t i = 0; i < n; ++i) { bodies[i].vx += ax[i] * dtHalf; bodies[i].vy += ay[i] * dtHalf; }
+        phase = 1;
+    }
+    void stepEnd() {     // :425-435
+        int64_t lo, hi;
+        mySlice(&lo, &hi);
+        BHTree* root = buildTree();
+        computeAccelerations(root, lo, hi);
+        const double t0 = now_ms();
+        const double dtHalf = par.dt * 0.5;
+        for (int64_t i = lo; i < hi; ++i) { bodies[i].vx += ax[i] * dtHalf; bodies[i].vy += ay[i] * dtHalf; }
         ctr.ms_integrate += now_ms() - t0;
         lastTree = root;
-        t0 = now_ms();
+        phase = 2;
+    }
+    void stepFinish() {  // :438
+        const double t0 = now_ms();
         mergeCloseBodiesIfNeeded();
         ctr.ms_merge += now_ms() - t0;
         ctr.total_steps++;
+        phase = 0;
     }
+    void step() { stepBegin(); stepEnd(); stepFinish(); }
 
     // data-class equals() used by bodies.indexOf(bi), BH.kt:522 (structural, bitwise on doubles)
     static bool structEq(const Body& a, const Body& b) { return std::memcmp(&a, &b, sizeof(Body)) == 0; }
@@ -485,6 +501,7 @@ int bh_get_positions_f32(bh_engine* e, int64_t cap, float* xy, float* m, int64_t
 
 int bh_step(bh_engine* e, int32_t nsteps) {
     if (!e || nsteps < 0) return fail(e, BH_E_ARG, "bh_step: bad arguments");
+    if (e->world > 1) return fail(e, BH_E_STATE, "bh_step: host-staged transport — drive the step with bh_step_begin / bh_step_end / bh_step_finish");
     const double t0 = now_ms();
     try { for (int s = 0; s < nsteps; ++s) e->step(); }
     catch (const std::bad_alloc&) { return fail(e, BH_E_OOM, "bh_step: out of memory"); }
@@ -620,7 +637,54 @@ int bh_get_body_counts(bh_engine* e, int32_t* interactions, int32_t* opened) {
 }
 
 int bh_comm_unique_id(void*, int32_t) { return BH_E_UNSUPPORTED; }
-int bh_comm_init(bh_engine* e, int32_t, int32_t, const void*, int32_t) { return fail(e, BH_E_UNSUPPORTED, "bh_comm_init: single-process reference port"); }
+int bh_comm_init(bh_engine* e, int32_t, int32_t, const void*, int32_t) { return fail(e, BH_E_UNSUPPORTED, "bh_comm_init: the reference port has no NCCL transport"); }
+int bh_comm_init_external(bh_engine* e, int32_t rank, int32_t world) {
+    if (!e || world < 1 || rank < 0 || rank >= world) return fail(e, BH_E_ARG, "bh_comm_init_external: bad arguments");
+    e->rank = rank; e->world = world;
+    return BH_OK;
+}
+int bh_step_begin(bh_engine* e) {
+    if (!e) return BH_E_ARG;
+    if (e->phase != 0) return fail(e, BH_E_STATE, "bh_step_begin: a step is already in progress");
+    try { e->stepBegin(); } catch (const std::bad_alloc&) { return fail(e, BH_E_OOM, "bh_step_begin: out of memory"); }
+    return BH_OK;
+}
+int bh_step_end(bh_engine* e) {
+    if (!e) return BH_E_ARG;
+    if (e->phase != 1) return fail(e, BH_E_STATE, "bh_step_end: call bh_step_begin first");
+    try { e->stepEnd(); } catch (const std::bad_alloc&) { return fail(e, BH_E_OOM, "bh_step_end: out of memory"); }
+    return BH_OK;
+}
+int bh_step_finish(bh_engine* e) {
+    if (!e) return BH_E_ARG;
+    if (e->phase != 2) return fail(e, BH_E_STATE, "bh_step_finish: call bh_step_end first");
+    e->stepFinish();
+    return BH_OK;
+}
+int bh_export_slice(bh_engine* e, int32_t field, int64_t cap, double* a, double* b, int64_t* lo_out, int64_t* hi_out) {
+    if (!e || (field != BH_FIELD_POS && field != BH_FIELD_VEL)) return fail(e, BH_E_ARG, "bh_export_slice: bad arguments");
+    int64_t lo, hi;
+    e->mySlice(&lo, &hi);
+    if (lo_out) *lo_out = lo;
+    if (hi_out) *hi_out = hi;
+    if (cap < hi - lo) return fail(e, BH_E_ARG, "bh_export_slice: capacity too small");
+    for (int64_t i = lo; i < hi; ++i) {
+        const Body& q = e->bodies[i];
+        if (a) a[i - lo] = field == BH_FIELD_POS ? q.x : q.vx;
+        if (b) b[i - lo] = field == BH_FIELD_POS ? q.y : q.vy;
+    }
+    return BH_OK;
+}
+int bh_import_slices(bh_engine* e, int32_t field, int64_t n, const double* a, const double* b) {
+    if (!e || (field != BH_FIELD_POS && field != BH_FIELD_VEL) || !a || !b) return fail(e, BH_E_ARG, "bh_import_slices: bad arguments");
+    if (n != (int64_t)e->bodies.size()) return fail(e, BH_E_ARG, "bh_import_slices: n must equal bh_num_bodies");
+    for (int64_t i = 0; i < n; ++i) {
+        Body& q = e->bodies[i];
+        if (field == BH_FIELD_POS) { q.x = a[i]; q.y = b[i]; } else { q.vx = a[i]; q.vy = b[i]; }
+    }
+    if (field == BH_FIELD_POS) e->lastTree = nullptr;
+    return BH_OK;
+}
 int bh_slice_bounds(int64_t n, int32_t world, int32_t rank, int64_t* lo, int64_t* hi) {
     if (n < 0 || world < 1 || rank < 0 || rank >= world || !lo || !hi) return BH_E_ARG;
     const int64_t per = (n + world - 1) / world;

@@ -154,8 +154,9 @@ def test_energy_drift_1000_steps(oracle_lib, cuda_lib):
     dg = abs(g.energy()["total"] - e0g) / abs(e0g)
     print("energy drift oracle", do, "gpu", dg)
     assert dg <= max(2.0 * do, 1e-4)
-    # momentum is conserved by the symmetric scheme to rounding (merge off)
-    assert abs(g.energy()["px"] - o.energy()["px"]) <= 1e-6 * max(1.0, abs(o.energy()["px"]))
+    # tree forces are not pairwise symmetric, so momentum drifts slightly and (the system being
+    # chaotic) differently for FP32 and f64 interactions; bound the difference, not the value
+    assert abs(g.energy()["px"] - o.energy()["px"]) <= 5e-3 * max(1.0, abs(o.energy()["px"]))
 
 
 def test_edge_cases(oracle_lib, cuda_lib):
@@ -234,3 +235,72 @@ def test_kotlin_facade_drives_the_engine(cuda_lib):
     eng.step()
     assert eng.getBodies() == []
     Config.reset()
+
+
+def _merge_scene(seed=41, n1=3000, n2=800, k=60):
+    """Two-disk scene whose heavy centres (m = 50,000 and 5,000 > mergeMaxMass) have satellites
+    inside the 8 px merge radius, plus a third heavy body close enough to be eaten itself."""
+    s = list(scenes.snap_f32(scenes.default_two_disks(n1=n1, n2=n2, seed=seed)))
+    rng = np.random.default_rng(seed)
+    ang, rad = rng.uniform(0, 2 * np.pi, k), rng.uniform(1.0, 7.0, k)
+    s[0][5:5 + k] = s[0][0] + rad * np.cos(ang)
+    s[1][5:5 + k] = s[1][0] + rad * np.sin(ang)
+    j = n1 + 3                                       # a satellite of the second disk near its centre n1
+    s[0][j], s[1][j] = s[0][n1] + 2.0, s[1][n1] - 3.0
+    s[0][n1 + 7], s[1][n1 + 7], s[4][n1 + 7] = s[0][n1] + 5.0, s[1][n1] + 1.0, 4500.0   # heavy, inside the radius of heavy n1
+    return tuple(np.ascontiguousarray(a) for a in s)
+
+
+def test_merge_rule_matches_oracle(oracle_lib, cuda_lib):
+    """mergeCloseBodiesIfNeeded (BH.kt:463-532) with the reference defaults (4000 / 8 px): the
+    same bodies disappear, masses are summed in the same order (bit-identical), list order is kept."""
+    scene = _merge_scene()
+    o = make_engine(oracle_lib, scene, theta=0.5, merge_min_dist=8.0)
+    g = make_engine(cuda_lib, scene, theta=0.5, merge_min_dist=8.0)
+    for step in range(6):
+        o.step(1)
+        g.step(1)
+        assert g.n == o.n, step
+        assert (g.get_origin() == o.get_origin()).all(), step
+        so, sg = o.get_bodies(), g.get_bodies()
+        assert (so[4] == sg[4]).all(), step                        # masses: same f64 sums, same order
+        # satellites 1-7 px from a 50,000-mass body feel a ~ 1e5-1e6: FP32 interaction rounding
+        # (1e-7 relative) moves them by ~1e-6 px per step; 1e-4 px is 4e-8 of the box
+        assert np.hypot(so[0] - sg[0], so[1] - sg[1]).max() < 1e-4
+    assert o.counters()["total_merged"] == g.counters()["total_merged"] > 40
+    # the engine keeps working on the shrunk list: accelerations still match
+    ax, ay = o.compute_accelerations()
+    gx, gy = g.compute_accelerations()
+    assert_acc_parity(ax, ay, gx, gy, "after merges")
+
+
+def test_merge_default_scene_long_run(oracle_lib, cuda_lib):
+    """The shipped app's configuration (merge on, θ = 0.30, Δt = 0.005): 60 steps, identical
+    survivor lists at every step."""
+    scene = scenes.snap_f32(scenes.default_two_disks(n1=2000, n2=500, seed=43))
+    o = make_engine(oracle_lib, scene, theta=0.30, merge_min_dist=8.0)
+    g = make_engine(cuda_lib, scene, theta=0.30, merge_min_dist=8.0)
+    for step in range(60):
+        o.step(1)
+        g.step(1)
+        assert g.n == o.n and (g.get_origin() == o.get_origin()).all(), step
+    assert (o.get_bodies()[4] == g.get_bodies()[4]).all()
+
+
+def test_rehoming_is_invisible_through_the_abi(cuda_lib):
+    """Device state lives in Morton ('home') order; the ABI speaks list order only.  Results must
+    not depend on how often the engine re-homes (bit-identical trajectories)."""
+    import bh_b200
+    scene = scenes.snap_f32(scenes.default_two_disks(n1=3000, n2=1000, seed=44))
+    outs = []
+    for interval in (1, 3, 1000):
+        e = bh_b200.NativeEngine(lib=cuda_lib, rehome_interval=interval, flags=1)
+        e.set_params(theta=0.5, merge_min_dist=0.0)
+        e.set_bodies(*scene)
+        e.step(7)
+        e.set_bodies(*e.get_bodies())          # same-length list: stored through the existing permutation
+        e.step(2)
+        outs.append(e.get_bodies() + (e.body_counts()[0],) + e.get_positions_f32())
+    for o in outs[1:]:
+        for a, b in zip(outs[0], o):
+            assert (a == b).all()
