@@ -33,8 +33,10 @@
 
 #if defined(__CUDACC__)
 #define BH_HD __host__ __device__ __forceinline__
+#define BH_HD_COLD __host__ __device__ __noinline__
 #else
 #define BH_HD inline
+#define BH_HD_COLD inline
 #endif
 
 #if !defined(__CUDACC__)
@@ -179,11 +181,14 @@ BH_HD int bh_prefix_shift(int levels, int d) { return 2 * (levels - d); }
 //   (xh, yh, m, s2)         centre of mass (hi parts), mass, (cell side)^2 as float;
 //                           s2 = -1 for a leaf or a zero-mass cell: always "accepted"
 //                           (no opening test for leaves, zero mass is pruned: BH.kt:216-221)
-//   (xl, yl, skip, level)   lo parts; preorder position after the subtree; depth
+//   (xl, yl, skip, band)    lo parts; preorder position after the subtree; half-width of the
+//                           band |theta^2 d^2 - s^2| <= band in which the FP32 opening test is
+//                           re-done in f64 (BH_GUARD_BAND * s^2; 0 for a leaf / zero-mass cell)
 struct alignas(32) BhCell {
     float xh, yh, m, s2;
     float xl, yl;
-    int   skip, level;
+    int   skip;
+    float band;
 };
 // Exact record: f64 centre of mass and mass, bit-identical to BHTree.computeMass
 // (BH.kt:173-202).  Read by the climb, by borderline opening tests and by the export.
@@ -289,9 +294,11 @@ BH_HD void bh_write_cell(const BhTreeView& t, int p, double cx, double cy, doubl
     bh_split(cx, &c.xh, &c.xl);
     bh_split(cy, &c.yh, &c.yl);
     c.m = (float)m;
-    c.s2 = (leaf || m == 0.0) ? -1.0f : (float)bh_side2(half, level);
+    const bool always = leaf || m == 0.0;
+    const float s2f = (float)bh_side2(half, level);
+    c.s2 = always ? -1.0f : s2f;
     c.skip = skip;
-    c.level = level;
+    c.band = always ? 0.0f : BH_GUARD_BAND * s2f;
     t.cell[p] = c;
 }
 
@@ -329,11 +336,10 @@ BH_HD void bh_climb_body(const BhTreeView& t, const BhRoot& root, int i, double 
 }
 
 struct BhWalkParams {
-    float  th2_lo, th2_hi;    // theta^2 * (1 -/+ guard band): FP32 sure-accept / sure-open bounds
+    float  th2f;              // theta^2 as float: the FP32 opening test is fma(d2, th2f, -s2) > 0
     float  soft2f;
     double theta2, soft2;     // BH.kt:378, Config.kt:20
     double half;              // root half-side
-    double side2[BH_MAX_LEVELS + 2];   // exact (2h)^2 per depth, BH.kt:226
 };
 
 BH_HD BhWalkParams bh_walk_params(double theta, double soft2, double half) {
@@ -341,10 +347,8 @@ BH_HD BhWalkParams bh_walk_params(double theta, double soft2, double half) {
     w.theta2 = theta * theta;   // BH.kt:378
     w.soft2 = soft2;
     w.half = half;
-    w.th2_lo = (float)(w.theta2 * (1.0 - (double)BH_GUARD_BAND));
-    w.th2_hi = (float)(w.theta2 * (1.0 + (double)BH_GUARD_BAND));
+    w.th2f = (float)w.theta2;
     w.soft2f = (float)soft2;
-    for (int d = 0; d < BH_MAX_LEVELS + 2; ++d) w.side2[d] = bh_side2(half, d);
     return w;
 }
 
@@ -353,78 +357,147 @@ struct BhWalkResult { double ax, ay; int interactions, opened, retests; };
 #ifndef BH_WALK_NEWTON
 #define BH_WALK_NEWTON 1      // one Newton step on MUFU.RSQ (device only)
 #endif
+#define BH_WALK_CHUNK 16      // visits between two folds of the FP32 partial sums into f64
+
+#if defined(__CUDA_ARCH__)
+// one 256-bit load of a whole 32-byte cell record (sm_100: LDG.E.256): one L1 wavefront per
+// distinct line instead of two
+__device__ __forceinline__ void bh_load_cell(const BhCell* __restrict__ c, float4* a, float4* b) {
+    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(a->x), "=f"(a->y), "=f"(a->z), "=f"(a->w), "=f"(b->x), "=f"(b->y), "=f"(b->z), "=f"(b->w)
+                 : "l"(c));
+}
+#endif
+
+// The reference's f64 opening test for a borderline cell (cold path), BH.kt:223-228 bit-for-bit.
+BH_HD_COLD bool bh_retest_cell(const BhCellD* __restrict__ cd, const BhCellS* __restrict__ sk, int p, double x, double y,
+                               double soft2, double theta2, double half) {
+    return bh_exact_accept(cd[p].comx, cd[p].comy, x, y, soft2, theta2, half, sk[p].level);
+}
+
+#if BH_WALK_NEWTON
+#define BH_WALK_NEWTON_ASM                                                                      \
+    "mul.f32 t2, inv, inv;\n\t"                                                                 \
+    "fma.rn.f32 t1, %7, t2, 0fC0400000;\n\t" /* d2*inv^2 - 3 */                                 \
+    "mul.f32 inv, inv, t1;\n\t"              /* -2 * refined rsqrt */
+#else
+#define BH_WALK_NEWTON_ASM ""
+#endif
+// second half of a visit: operands  %0 fx  %1 fy  %2 interactions  %3 opened  %4 p  |  %5 t  %6 self
+// %7 d2  %8 m  %9 dx  %10 dy  %11 skip
+#define BH_WALK_VISIT_ASM()                                                                     \
+    asm volatile(                                                                               \
+        "{\n\t"                                                                                 \
+        ".reg .pred P0, P1;\n\t"                                                                \
+        ".reg .f32 inv, t1, t2, wg;\n\t"                                                        \
+        ".reg .s32 p1;\n\t"                                                                     \
+        "setp.gt.f32 P0, %5, 0f00000000;\n\t"          /* accept                          */    \
+        "setp.ne.and.s32 P1, %4, %6, P0;\n\t"          /* ... and not the body's own leaf */    \
+        "setp.neu.and.f32 P1, %8, 0f00000000, P1;\n\t" /* ... and mass != 0 (BH.kt:216)   */    \
+        "rsqrt.approx.ftz.f32 inv, %7;\n\t"                                                     \
+        BH_WALK_NEWTON_ASM                                                                      \
+        "mul.f32 wg, %8, inv;\n\t"                                                              \
+        "mul.f32 wg, wg, inv;\n\t"                                                              \
+        "mul.f32 wg, wg, inv;\n\t"                                                              \
+        "@P1 fma.rn.f32 %0, wg, %9, %0;\n\t"                                                    \
+        "@P1 fma.rn.f32 %1, wg, %10, %1;\n\t"                                                   \
+        "@P1 add.s32 %2, %2, 1;\n\t"                                                            \
+        "@!P0 add.s32 %3, %3, 1;\n\t"                                                           \
+        "add.s32 p1, %4, 1;\n\t"                                                                \
+        "selp.s32 %4, %11, p1, P0;\n\t"                                                         \
+        "}"                                                                                     \
+        : "+f"(fx), "+f"(fy), "+r"(ni), "+r"(no), "+r"(p)                                       \
+        : "f"(tt), "r"(self), "f"(d2), "f"(a.z), "f"(dx), "f"(dy), "r"(__float_as_int(b.z)))
 
 // accumulateForce (BH.kt:215-239) for one body, stackless over the preorder array.
 // `self` = preorder position of the body's own leaf (-1 if it is not in the tree).
-// Per-body decisions are the reference's: the FP32 test decides outside a 1e-5 guard band,
-// the exact f64 expression inside it.  Interaction math is FP32 on (hi,lo)-split coordinate
-// differences; FP32 partial sums are folded into f64 accumulators every 16 visits (the lanes
-// of a warp share the visit counter, so the fold is a uniform branch).
-// Returns sum m*d/r^3 (G is applied by the caller).
-// ZERO_MASS = false skips the "mass != 0" test of the interaction counter (the host knows
-// whether any body has zero mass).
-template <bool ZERO_MASS>
-BH_HD BhWalkResult bh_walk_body(const BhTreeView& t, const BhWalkParams& w, double x, double y, int self) {
+// Per-body decisions are the reference's: the FP32 test t = theta^2 d^2 - s^2 > 0 decides unless
+// |t| is inside the cell's guard band, where the exact f64 expression decides.  Interaction math
+// is FP32 on (hi,lo)-split coordinate differences; FP32 partial sums are folded into f64
+// accumulators every BH_WALK_CHUNK visits.  Returns sum m*d/r^3 (G is applied by the caller).
+//
+// Device form.  Every lane of the warp must call this (`active` = false for surplus lanes).  A
+// visit is branch-free apart from the rare f64 re-test (an opened cell simply does not
+// accumulate), so lanes that disagree on accept/open do not serialise; a lane that has finished
+// idles on the terminal record cell[M] (mass 0, always accepted, skip = M) until the whole warp
+// is done, so there is no per-visit exit test either.  One visit is ~31 SASS instructions: one
+// 256-bit load, 6 FADD + 2 FFMA for the split difference and d^2, FFMA + 2 FSETP for the test,
+// MUFU.RSQ + one Newton step written as ic = inv*(d2*inv^2 - 3) (= -2 x the refined 1/sqrt; the
+// factor (-2)^3 is divided out exactly at the end), 3 FMUL for m*ic^3, predicated accumulation
+// and counters, and the skip/next select.
+BH_HD BhWalkResult bh_walk_body(const BhTreeView& t, const BhWalkParams& w, double x, double y, int self, bool active,
+                                int zero = 0) {
     float xh, xl, yh, yl;
     bh_split(x, &xh, &xl);
     bh_split(y, &yh, &yl);
     BH_OPAQUE_F(xh); BH_OPAQUE_F(xl); BH_OPAQUE_F(yh); BH_OPAQUE_F(yl);   // keep the F2F out of the loop
     BhWalkResult r; r.ax = 0.0; r.ay = 0.0; r.interactions = 0; r.opened = 0; r.retests = 0;
-    float fx = 0.f, fy = 0.f;
-    int p = 0;
+    const float th2 = w.th2f, soft2 = w.soft2f;
+    const BhCell* __restrict__ cells = t.cell;
     const int M = t.M;
-    const float4* __restrict__ cells = reinterpret_cast<const float4*>(t.cell);
-    while (p < M) {
-#pragma unroll 1
-        for (int k = 0; k < 16; ++k) {
+    int p = active ? 0 : M;
 #if defined(__CUDA_ARCH__)
-            const float4 a = __ldg(cells + 2 * (size_t)p);
-            const float4 b = __ldg(cells + 2 * (size_t)p + 1);
-            const int skip = __float_as_int(b.z);
-#else
-            const float4 a = cells[2 * (size_t)p];
-            const float4 b = cells[2 * (size_t)p + 1];
-            const int skip = t.cell[p].skip;
-#endif
+    // `zero` is a 0 the compiler cannot see through (loaded from memory): it keeps the base
+    // pointer in registers instead of re-loading it from the constant bank at every visit
+    cells += zero;
+    int ni = 0, no = 0;
+    while (__any_sync(0xffffffffu, p < M)) {
+        float fx = 0.f, fy = 0.f;
+#pragma unroll
+        for (int k = 0; k < BH_WALK_CHUNK; ++k) {
+            float4 a, b;
+            bh_load_cell(cells + p, &a, &b);
             const float dx = (a.x - xh) + (b.x - xl);
             const float dy = (a.y - yh) + (b.y - yl);
-            const float d2 = fmaf(dx, dx, fmaf(dy, dy, w.soft2f));
-            bool accept = a.w < d2 * w.th2_lo;
-            if (!accept && !(a.w > d2 * w.th2_hi)) {   // borderline: the reference's f64 test decides
-#if defined(__CUDA_ARCH__)
-                const int level = __float_as_int(b.w);
-#else
-                const int level = t.cell[p].level;
-#endif
-                // BH.kt:223-228 bit-for-bit (f64, no contraction)
-                const BhCellD e = t.cd[p];
-                const double ex = BH_DSUB(e.comx, x), ey = BH_DSUB(e.comy, y);
-                const double dist2 = BH_DADD(BH_DADD(BH_DMUL(ex, ex), BH_DMUL(ey, ey)), w.soft2);
-                accept = w.side2[level] < BH_DMUL(w.theta2, dist2);
+            const float d2 = fmaf(dx, dx, fmaf(dy, dy, soft2));
+            float tt = fmaf(d2, th2, -a.w);
+            if (fabsf(tt) <= b.w) {   // borderline: the reference's f64 test decides
+                tt = bh_retest_cell(t.cd, t.sk, p, x, y, w.soft2, w.theta2, w.half) ? 1.0f : -1.0f;
                 r.retests++;
             }
-            if (accept) {
-                if (p != self) {
-                    float inv = BH_RSQRTF(d2);
-#if defined(__CUDA_ARCH__) && BH_WALK_NEWTON
-                    inv = inv * fmaf(-0.5f * d2, inv * inv, 1.5f);
+            BH_WALK_VISIT_ASM();
+        }
+        r.ax += (double)fx; r.ay += (double)fy;
+    }
+    r.interactions = ni; r.opened = no;
+#if BH_WALK_NEWTON
+    r.ax *= -0.125; r.ay *= -0.125;   // (-2)^3 from the Newton form above; exact (power of two)
 #endif
-                    const float wgt = a.z * inv * inv * inv;
-                    fx = fmaf(wgt, dx, fx);
-                    fy = fmaf(wgt, dy, fy);
-                    r.interactions += ZERO_MASS ? (a.z != 0.0f) : 1;
-                }
-                p = skip;
-            } else {
-                r.opened++;
-                p = p + 1;
+#else
+    while (p < M) {
+        float fx = 0.f, fy = 0.f;
+        for (int k = 0; k < BH_WALK_CHUNK; ++k) {
+            const BhCell& c = cells[p];
+            const float dx = (c.xh - xh) + (c.xl - xl);
+            const float dy = (c.yh - yh) + (c.yl - yl);
+            const float d2 = fmaf(dx, dx, fmaf(dy, dy, soft2));
+            const float tt = fmaf(d2, th2, -c.s2);
+            bool accept = tt > 0.0f;
+            if (fabsf(tt) <= c.band) {   // borderline: the reference's f64 test decides
+                accept = bh_retest_cell(t.cd, t.sk, p, x, y, w.soft2, w.theta2, w.half);
+                r.retests++;
             }
+            const float inv = BH_RSQRTF(d2);
+            const bool use = accept && (p != self) && (c.m != 0.0f);
+            const float wgt = use ? c.m * inv * inv * inv : 0.0f;
+            fx = fmaf(wgt, dx, fx);
+            fy = fmaf(wgt, dy, fy);
+            r.interactions += use;
+            r.opened += !accept;
+            p = accept ? c.skip : p + 1;
             if (p >= M) break;
         }
-        // every lane of a warp is at the same k: the fold is a uniform branch
-        r.ax += (double)fx; r.ay += (double)fy; fx = 0.f; fy = 0.f;
+        r.ax += (double)fx; r.ay += (double)fy;
     }
+#endif
     return r;
+}
+
+// the terminal record cell[M] finished lanes idle on
+BH_HD void bh_write_terminal_cell(const BhTreeView& t) {
+    BhCell c;
+    c.xh = 0.f; c.yh = 0.f; c.m = 0.f; c.s2 = -1.0f; c.xl = 0.f; c.yl = 0.f; c.skip = t.M; c.band = 0.0f;
+    t.cell[t.M] = c;
 }
 
 #endif  // BH_CORE_H

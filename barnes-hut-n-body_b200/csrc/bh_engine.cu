@@ -316,7 +316,7 @@ struct bh_engine {
         n_in = sc_host->n_in; n_internal = sc_host->n_internal; M = n_in + n_internal;
         ctr.n_in_tree = n_in; ctr.n_out_of_box = n - n_in; ctr.n_internal = n_internal; ctr.n_cells = M;
         ctr.n_jitter_bodies = sc_host->n_jitter; ctr.max_depth = sc_host->max_depth; ctr.key_levels = root.levels;
-        BH_RC(ensure_cells(M));
+        BH_RC(ensure_cells((int64_t)M + 1));   // + the terminal record the walk idles on
         if (nn > 0) BH_TRY(cudaMemsetAsync(leafpos, 0xFF, (size_t)nn * sizeof(int), st));   // -1: not in the tree
         if (n_in > 0) {
             BH_TRY(cudaMemsetAsync(arrived, 0, (size_t)M * sizeof(int), st));
@@ -363,10 +363,7 @@ struct bh_engine {
         if (count > 0) {
             const BhWalkParams w = bh_walk_params(par.theta, par.soft2, par.root_half);
             const int g = grid_for(count, 128);
-            if (any_zero_mass)
-                k_walk<true><<<g, 128, 0, st>>>(view(), w, (int)first, (int)count, x, y, m, leafpos, par.G, ax, ay, cntI, cntO, sc(), tot);
-            else
-                k_walk<false><<<g, 128, 0, st>>>(view(), w, (int)first, (int)count, x, y, m, leafpos, par.G, ax, ay, cntI, cntO, sc(), tot);
+            k_walk<<<g, 128, 0, st>>>(view(), w, (int)first, (int)count, x, y, m, leafpos, par.G, ax, ay, cntI, cntO, sc(), tot);
             ctr.kernel_launches += 1;
         }
         BH_TRY(cudaEventRecord(ev[slot + 3], st));

@@ -180,6 +180,7 @@ __global__ void __launch_bounds__(256) k_climb(BhTreeView t, BhRoot root, const 
     if (i >= t.n_in) return;
     const int b = t.order[i];
     leafpos[b] = t.S[i + 1] + i;
+    if (i == 0) bh_write_terminal_cell(t);
     bh_climb_body(t, root, i, x[b], y[b], m[b]);
 }
 
@@ -187,7 +188,6 @@ __global__ void __launch_bounds__(256) k_climb(BhTreeView t, BhRoot root, const 
 // Targets are the bodies [first_target, first_target + n_targets) in HOME order, which is the
 // Morton order of the last re-homing, so the lanes of a warp are spatial neighbours and the
 // body reads / acceleration writes are coalesced.  Stackless over the preorder cells.
-template <bool ZERO_MASS>
 __global__ void __launch_bounds__(128)
 k_walk(BhTreeView t, BhWalkParams w, int first_target, int n_targets, const double* __restrict__ x,
        const double* __restrict__ y, const double* __restrict__ m, const int* __restrict__ leafpos, double G,
@@ -195,13 +195,10 @@ k_walk(BhTreeView t, BhWalkParams w, int first_target, int n_targets, const doub
        DevScalars* __restrict__ sc, DevTotals* __restrict__ tot) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     int ni = 0, no = 0, nr = 0;
-    // every lane enters the walk (it contains full-warp shuffles); surplus lanes see an empty tree
+    // every lane enters the walk (it contains full-warp votes); surplus lanes idle on the terminal record
     const bool active = k < n_targets;
     const int b = first_target + (active ? k : 0);
-    const int self = leafpos[b];
-    BhTreeView tv = t;
-    if (!active) tv.M = 0;
-    const BhWalkResult r = bh_walk_body<ZERO_MASS>(tv, w, x[b], y[b], self);
+    const BhWalkResult r = bh_walk_body(t, w, x[b], y[b], leafpos[b], active, (int)sc->pad);
     if (active) {
         const double mb = m[b];
         // BH.kt:390-391 divides the force by b.m: a zero-mass body gets 0/0 = NaN

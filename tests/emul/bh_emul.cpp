@@ -72,7 +72,7 @@ int bh_emul_accelerations(int n, const double* x, const double* y, const double*
     for (int si = 0; si < n; ++si) {
         const int b = e.order[si];
         const int self = si < e.n_in ? e.S[si + 1] + si : -1;
-        BhWalkResult r = bh_walk_body<true>(t, w, x[b], y[b], self);
+        BhWalkResult r = bh_walk_body(t, w, x[b], y[b], self, true);
         if (ax) ax[b] = (m[b] == 0.0) ? NAN : G * (double)r.ax;
         if (ay) ay[b] = (m[b] == 0.0) ? NAN : G * (double)r.ay;
         if (cntI) cntI[b] = r.interactions;
