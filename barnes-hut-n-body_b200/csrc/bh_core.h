@@ -500,4 +500,163 @@ BH_HD void bh_write_terminal_cell(const BhTreeView& t) {
     t.cell[t.M] = c;
 }
 
+// ---- group walk: G bodies per thread, one shared preorder position ---------------------------
+// The per-lane walk above is bound by the L1 data stage: every lane of a warp is at a different
+// cell, so one warp-wide load touches ~15 distinct 32 B sectors.  Here a THREAD walks for G
+// Morton-consecutive bodies at once: the cell is loaded once and tested against the G bodies
+// (G independent dependency chains: instruction-level parallelism instead of occupancy).  The
+// per-body decisions stay the reference's: a cell is opened when ANY un-muted body of the group
+// opens it; a body that accepts a cell the group opens takes the interaction and is muted
+// (`mute` = skip of that cell) until the walk leaves the subtree.  The group visits the union of
+// its bodies' cells, ~1.14x the visits of one body for G = 4 (probe: bh_emul_group_stats), and a
+// warp-wide load now serves 32*G body visits.
+template <int G>
+struct BhGroupResult {
+    double ax[G], ay[G];
+    int interactions[G], opened[G];
+    int retests;
+};
+
+// second half of one body's share of a group visit: operands  %0 fx  %1 fy  %2 interactions
+// %3 opened  %4 mute  %5 gmin  |  %6 t  %7 p  %8 self  %9 d2  %10 m  %11 dx  %12 dy  %13 skip
+// gmin = NaN-ignoring minimum of the un-muted bodies' t: the group opens the cell iff gmin < 0.
+#define BH_GROUP_BODY_ASM(ZM)                                                                   \
+    asm volatile(                                                                               \
+        "{\n\t"                                                                                 \
+        ".reg .pred Pu, P0, Pw, P1;\n\t"                                                        \
+        ".reg .f32 te, inv, t1, t2, wg;\n\t"                                                    \
+        "setp.ge.s32 Pu, %7, %4;\n\t"                  /* un-muted                         */   \
+        "selp.f32 te, %6, 0f7FC00000, Pu;\n\t"         /* muted: neither accepts nor opens */   \
+        "setp.gt.f32 P0, te, 0f00000000;\n\t"          /* accepts                          */   \
+        "setp.lt.f32 Pw, te, 0f00000000;\n\t"          /* wants the cell opened            */   \
+        "min.f32 %5, %5, te;\n\t"                                                               \
+        "setp.ne.and.s32 P1, %7, %8, P0;\n\t"          /* ... and not the body's own leaf  */   \
+        ZM                                                                                      \
+        "rsqrt.approx.ftz.f32 inv, %9;\n\t"                                                     \
+        BH_GROUP_NEWTON_ASM                                                                     \
+        "mul.f32 wg, %10, inv;\n\t"                                                             \
+        "mul.f32 wg, wg, inv;\n\t"                                                              \
+        "mul.f32 wg, wg, inv;\n\t"                                                              \
+        "@P1 fma.rn.f32 %0, wg, %11, %0;\n\t"                                                   \
+        "@P1 fma.rn.f32 %1, wg, %12, %1;\n\t"                                                   \
+        "@P1 add.s32 %2, %2, 1;\n\t"                                                            \
+        "@Pw add.s32 %3, %3, 1;\n\t"                                                            \
+        "@P0 mov.s32 %4, %13;\n\t"                     /* muted until the walk leaves the cell */ \
+        "}"                                                                                     \
+        : "+f"(fx[j]), "+f"(fy[j]), "+r"(ni[j]), "+r"(no[j]), "+r"(mute[j]), "+f"(gmin)         \
+        : "f"(tt[j]), "r"(p), "r"(slf[j]), "f"(d2[j]), "f"(a.z), "f"(dx[j]), "f"(dy[j]), "r"(skip))
+#if BH_WALK_NEWTON
+#define BH_GROUP_NEWTON_ASM                                                                     \
+    "mul.f32 t2, inv, inv;\n\t"                                                                 \
+    "fma.rn.f32 t1, %9, t2, 0fC0400000;\n\t"                                                    \
+    "mul.f32 inv, inv, t1;\n\t"
+#else
+#define BH_GROUP_NEWTON_ASM ""
+#endif
+
+template <int G, bool ZERO_MASS>
+BH_HD void bh_walk_group(const BhTreeView& t, const BhWalkParams& w, const double* x, const double* y, const int* self,
+                         int nactive, int zero, BhGroupResult<G>* out) {
+    float xh[G], xl[G], yh[G], yl[G], fx[G], fy[G];
+    double sx[G], sy[G];
+    int ni[G], no[G], mute[G], slf[G];
+#pragma unroll
+    for (int j = 0; j < G; ++j) {
+        bh_split(x[j], &xh[j], &xl[j]);
+        bh_split(y[j], &yh[j], &yl[j]);
+        BH_OPAQUE_F(xh[j]); BH_OPAQUE_F(xl[j]); BH_OPAQUE_F(yh[j]); BH_OPAQUE_F(yl[j]);
+        sx[j] = 0.0; sy[j] = 0.0; ni[j] = 0; no[j] = 0;
+        mute[j] = (j < nactive) ? 0 : 0x7fffffff;     // surplus slots stay muted for ever
+        slf[j] = self[j];
+    }
+    int retests = 0;
+    const float th2 = w.th2f, soft2 = w.soft2f;
+    const BhCell* __restrict__ cells = t.cell + zero;   // `zero`: see bh_walk_body
+    const int M = t.M;
+    int p = nactive > 0 ? 0 : M;
+    int gv = 0, iters = 0;                              // real group visits / all iterations
+#if defined(__CUDA_ARCH__)
+    while (__any_sync(0xffffffffu, p < M)) {
+#pragma unroll
+        for (int j = 0; j < G; ++j) { fx[j] = 0.f; fy[j] = 0.f; }
+#pragma unroll 2
+        for (int k = 0; k < BH_WALK_CHUNK; ++k) {
+            float4 a, b;
+            bh_load_cell(cells + p, &a, &b);
+            const int skip = __float_as_int(b.z);
+            float dx[G], dy[G], d2[G], tt[G];
+            bool border = false;
+#pragma unroll
+            for (int j = 0; j < G; ++j) {
+                dx[j] = (a.x - xh[j]) + (b.x - xl[j]);
+                dy[j] = (a.y - yh[j]) + (b.y - yl[j]);
+                d2[j] = fmaf(dx[j], dx[j], fmaf(dy[j], dy[j], soft2));
+                tt[j] = fmaf(d2[j], th2, -a.w);
+                border |= fabsf(tt[j]) <= b.w;
+            }
+            if (border) {   // some body is inside the guard band: the reference's f64 test decides
+#pragma unroll
+                for (int j = 0; j < G; ++j)
+                    if (fabsf(tt[j]) <= b.w) {
+                        tt[j] = bh_retest_cell(t.cd, t.sk, p, x[j], y[j], w.soft2, w.theta2, w.half) ? 1.0f : -1.0f;
+                        retests += (p >= mute[j]);
+                    }
+            }
+            float gmin = 1.0f;
+#pragma unroll
+            for (int j = 0; j < G; ++j) {
+                if (ZERO_MASS) { BH_GROUP_BODY_ASM("setp.neu.and.f32 P1, %10, 0f00000000, P1;\n\t"); }
+                else { BH_GROUP_BODY_ASM(""); }
+            }
+            gv += (p < M);
+            p = (gmin < 0.0f) ? p + 1 : skip;
+        }
+        iters += BH_WALK_CHUNK;
+#pragma unroll
+        for (int j = 0; j < G; ++j) { sx[j] += (double)fx[j]; sy[j] += (double)fy[j]; }
+    }
+#else
+    while (p < M) {
+        const BhCell& c = cells[p];
+        bool gopen = false;
+        for (int j = 0; j < G; ++j) {
+            const float dx = (c.xh - xh[j]) + (c.xl - xl[j]);
+            const float dy = (c.yh - yh[j]) + (c.yl - yl[j]);
+            const float d2 = fmaf(dx, dx, fmaf(dy, dy, soft2));
+            const float tt = fmaf(d2, th2, -c.s2);
+            const bool unmuted = p >= mute[j];
+            bool acc = tt > 0.0f;
+            if (fabsf(tt) <= c.band) {
+                acc = bh_retest_cell(t.cd, t.sk, p, x[j], y[j], w.soft2, w.theta2, w.half);
+                retests += unmuted;
+            }
+            if (!unmuted) continue;
+            if (!acc) { gopen = true; no[j]++; continue; }
+            const float ic = BH_RSQRTF(d2);
+            if (p != slf[j] && (!ZERO_MASS || c.m != 0.0f)) {
+                const float wg = c.m * ic * ic * ic;
+                sx[j] += (double)(wg * dx); sy[j] += (double)(wg * dy);
+                ni[j]++;
+            }
+            mute[j] = c.skip;
+        }
+        ++gv; ++iters;
+        p = gopen ? p + 1 : c.skip;
+    }
+    (void)fx; (void)fy;
+#endif
+#pragma unroll
+    for (int j = 0; j < G; ++j) {
+#if defined(__CUDA_ARCH__) && BH_WALK_NEWTON
+        out->ax[j] = sx[j] * -0.125; out->ay[j] = sy[j] * -0.125;
+#else
+        out->ax[j] = sx[j]; out->ay[j] = sy[j];
+#endif
+        // idle iterations on the terminal record were counted as interactions unless ZERO_MASS
+        out->interactions[j] = (j < nactive) ? ni[j] - (ZERO_MASS ? 0 : (iters - gv)) : 0;
+        out->opened[j] = no[j];
+    }
+    out->retests = retests;
+}
+
 #endif  // BH_CORE_H

@@ -331,6 +331,7 @@ struct bh_engine {
         return BH_OK;
     }
     int64_t ctr_rehomes = 0;
+    int walk_group_min_waves = 0;   // BH_WALK_GROUP_MIN_WAVES > 0: group walk from this many waves of 128-thread blocks per SM
 
     int sort_pairs(int nn, int key_bits) {
         // the sort zeroes nothing itself here: build() already cleared the scratch region
@@ -362,8 +363,18 @@ struct bh_engine {
         BH_TRY(cudaEventRecord(ev[slot + 2], st));
         if (count > 0) {
             const BhWalkParams w = bh_walk_params(par.theta, par.soft2, par.root_half);
-            const int g = grid_for(count, 128);
-            k_walk<<<g, 128, 0, st>>>(view(), w, (int)first, (int)count, x, y, m, leafpos, par.G, ax, ay, cntI, cntO, sc(), tot);
+            // experimental 4-bodies-per-thread walk (see bh_walk_group): same speed as the per-lane
+            // walk on B200 at 1M bodies (issue-bound instead of L1-data-stage-bound), so off by default
+            if (walk_group_min_waves > 0 && count >= (int64_t)num_sms * 128 * WALK_G * walk_group_min_waves) {
+                const int g = grid_for((count + WALK_G - 1) / WALK_G, 128);
+                if (any_zero_mass)
+                    k_walk_group<true><<<g, 128, 0, st>>>(view(), w, (int)first, (int)count, x, y, m, leafpos, par.G, ax, ay, cntI, cntO, sc(), tot);
+                else
+                    k_walk_group<false><<<g, 128, 0, st>>>(view(), w, (int)first, (int)count, x, y, m, leafpos, par.G, ax, ay, cntI, cntO, sc(), tot);
+            } else {
+                const int g = grid_for(count, 128);
+                k_walk<<<g, 128, 0, st>>>(view(), w, (int)first, (int)count, x, y, m, leafpos, par.G, ax, ay, cntI, cntO, sc(), tot);
+            }
             ctr.kernel_launches += 1;
         }
         BH_TRY(cudaEventRecord(ev[slot + 3], st));
@@ -505,6 +516,7 @@ int bh_create(const bh_config* cfg, bh_engine** out) {
     e->device = e->cfg.device;
     e->rehome_interval = e->cfg.rehome_interval > 0 ? e->cfg.rehome_interval : 8;
     if (const char* s = getenv("BH_REHOME_INTERVAL")) { const int v = atoi(s); if (v > 0) e->rehome_interval = v; }
+    if (const char* s = getenv("BH_WALK_GROUP_MIN_WAVES")) e->walk_group_min_waves = atoi(s);
     cudaError_t ce = cudaSetDevice(e->device);
     if (ce == cudaSuccess) ce = cudaStreamCreateWithFlags(&e->st, cudaStreamNonBlocking);
     for (int k = 0; k < 16 && ce == cudaSuccess; ++k) ce = cudaEventCreate(&e->ev[k]);

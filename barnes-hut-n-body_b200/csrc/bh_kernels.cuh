@@ -222,6 +222,55 @@ k_walk(BhTreeView t, BhWalkParams w, int first_target, int n_targets, const doub
     }
 }
 
+// The same evaluation with WALK_G bodies per thread (bh_walk_group): used when there are enough
+// targets to fill the machine with a quarter of the threads.
+constexpr int WALK_G = 4;
+template <bool ZERO_MASS>
+__global__ void __launch_bounds__(128)
+k_walk_group(BhTreeView t, BhWalkParams w, int first_target, int n_targets, const double* __restrict__ x,
+             const double* __restrict__ y, const double* __restrict__ m, const int* __restrict__ leafpos, double G,
+             double* __restrict__ ax, double* __restrict__ ay, int* __restrict__ cntI, int* __restrict__ cntO,
+             DevScalars* __restrict__ sc, DevTotals* __restrict__ tot) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    const int rel = k * WALK_G;
+    int nactive = n_targets - rel;
+    nactive = nactive < 0 ? 0 : (nactive > WALK_G ? WALK_G : nactive);
+    double bx[WALK_G], by[WALK_G];
+    int self[WALK_G];
+#pragma unroll
+    for (int j = 0; j < WALK_G; ++j) {
+        const int b = first_target + (j < nactive ? rel + j : 0);
+        bx[j] = x[b]; by[j] = y[b]; self[j] = leafpos[b];
+    }
+    BhGroupResult<WALK_G> r;
+    bh_walk_group<WALK_G, ZERO_MASS>(t, w, bx, by, self, nactive, (int)sc->pad, &r);
+    int ni = 0, no = 0, nr = r.retests;
+#pragma unroll
+    for (int j = 0; j < WALK_G; ++j) {
+        if (j < nactive) {
+            const int b = first_target + rel + j;
+            const double mb = m[b];
+            ax[b] = (mb == 0.0) ? nan("") : G * r.ax[j];    // BH.kt:390-391: 0/0 = NaN for m == 0
+            ay[b] = (mb == 0.0) ? nan("") : G * r.ay[j];
+            ni += r.interactions[j]; no += r.opened[j];
+            if (cntI) { cntI[b] = r.interactions[j]; cntO[b] = r.opened[j]; }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        ni += __shfl_xor_sync(0xffffffffu, ni, o);
+        no += __shfl_xor_sync(0xffffffffu, no, o);
+        nr += __shfl_xor_sync(0xffffffffu, nr, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(&sc->interactions, (unsigned long long)ni);
+        atomicAdd(&sc->opened, (unsigned long long)no);
+        atomicAdd(&tot->interactions, (unsigned long long)ni);
+        atomicAdd(&tot->opened, (unsigned long long)no);
+        if (nr) { atomicAdd(&sc->retests, (unsigned long long)nr); atomicAdd(&tot->retests, (unsigned long long)nr); }
+    }
+}
+
 // BH.kt:411-422 / :429-432 in f64 with the reference's rounding (no FMA contraction):
 //   v += a * dtHalf ; if (drift) x += v * dt
 __global__ void __launch_bounds__(256)

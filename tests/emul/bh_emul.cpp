@@ -137,3 +137,99 @@ extern "C" int bh_emul_union_stats(int n, const double* x, const double* y, cons
     out[0] = sumU / groups; out[1] = sumMax / groups; out[2] = sumMean / groups; out[3] = groups;
     return 0;
 }
+
+// ---- design probe (not a test): L1 sectors touched per warp iteration of the per-lane walk when
+// lanes may only run ahead of the slowest lane by `window` preorder positions (window <= 0: free
+// running).  out = {iterations per warp, distinct 32B sectors per iteration, distinct 128B lines
+// per iteration, sum over iterations of max(floor, sectors) per warp, lane-visits per warp}
+extern "C" int bh_emul_window_stats(int n, const double* x, const double* y, const double* m, double rcx, double rcy,
+                                    double rhalf, double theta, double soft2, int window, int floor_cost, int stride,
+                                    double* out /*[5]*/) {
+    Emul e;
+    build(e, n, x, y, m, rcx, rcy, rhalf);
+    const double theta2 = theta * theta;
+    const int G = 32;
+    double it = 0, sec = 0, lin = 0, cost = 0, vis = 0;
+    int groups = 0;
+    for (int g0 = 0; g0 + G <= e.n_in; g0 += G * stride, ++groups) {
+        int p[G];
+        for (int l = 0; l < G; ++l) p[l] = 0;
+        for (;;) {
+            int pmin = e.M;
+            for (int l = 0; l < G; ++l) pmin = std::min(pmin, p[l]);
+            if (pmin >= e.M) break;
+            int seen[G], ns = 0, lseen[G], nl = 0;
+            for (int l = 0; l < G; ++l) {
+                if (p[l] >= e.M) continue;
+                if (window > 0 && p[l] >= pmin + window) continue;   // waits
+                const int q = p[l];
+                bool dup = false;
+                for (int k = 0; k < ns; ++k) dup |= seen[k] == q;
+                if (!dup) seen[ns++] = q;
+                dup = false;
+                for (int k = 0; k < nl; ++k) dup |= lseen[k] == (q >> 2);
+                if (!dup) lseen[nl++] = q >> 2;
+                const int b = e.order[g0 + l];
+                const bool leafish = e.cell[q].s2 < 0;
+                const bool acc = leafish || bh_exact_accept(e.cd[q].comx, e.cd[q].comy, x[b], y[b], soft2, theta2, rhalf, e.sk[q].level);
+                p[l] = acc ? e.sk[q].skip : q + 1;
+                vis += 1;
+            }
+            it += 1; sec += ns; lin += nl; cost += std::max(floor_cost, ns);
+        }
+    }
+    out[0] = it / groups; out[1] = sec / it; out[2] = lin / it; out[3] = cost / groups; out[4] = vis / groups;
+    return 0;
+}
+
+// ---- design probe (not a test): the warp split into groups of `group` lanes that walk in
+// lockstep (one shared position per group: a cell is opened when any un-muted lane of the group
+// opens it; a lane that accepts a cell its group opens takes the interaction and is muted until the
+// walk leaves that subtree).  Per-body decisions are unchanged.  out = {iterations per warp,
+// distinct sectors per iteration, sum over iterations of max(floor, sectors) per warp,
+// group-visits per warp, useful lane-visits per warp}
+extern "C" int bh_emul_group_stats(int n, const double* x, const double* y, const double* m, double rcx, double rcy,
+                                   double rhalf, double theta, double soft2, int group, int floor_cost, int stride,
+                                   double* out /*[5]*/) {
+    Emul e;
+    build(e, n, x, y, m, rcx, rcy, rhalf);
+    const double theta2 = theta * theta;
+    const int G = 32, NG = G / group;
+    double it = 0, sec = 0, cost = 0, gvis = 0, lvis = 0;
+    int warps = 0;
+    for (int g0 = 0; g0 + G <= e.n_in; g0 += G * stride, ++warps) {
+        int p[G], mute[G];
+        for (int g = 0; g < NG; ++g) p[g] = 0;
+        for (int l = 0; l < G; ++l) mute[l] = 0;
+        for (;;) {
+            bool any = false;
+            int seen[G], ns = 0;
+            for (int g = 0; g < NG; ++g) {
+                const int q = p[g];
+                if (q >= e.M) continue;
+                any = true;
+                bool dup = false;
+                for (int k = 0; k < ns; ++k) dup |= seen[k] == q;
+                if (!dup) seen[ns++] = q;
+                bool open = false;
+                bool acc[G];
+                for (int j = 0; j < group; ++j) {
+                    const int l = g * group + j;
+                    const int b = e.order[g0 + l];
+                    const bool leafish = e.cell[q].s2 < 0;
+                    acc[j] = leafish || bh_exact_accept(e.cd[q].comx, e.cd[q].comy, x[b], y[b], soft2, theta2, rhalf, e.sk[q].level);
+                    if (q >= mute[l]) { lvis += 1; if (!acc[j]) open = true; }
+                }
+                if (open) {
+                    for (int j = 0; j < group; ++j) { const int l = g * group + j; if (q >= mute[l] && acc[j]) mute[l] = e.sk[q].skip; }
+                    p[g] = q + 1;
+                } else p[g] = e.sk[q].skip;
+                gvis += 1;
+            }
+            if (!any) break;
+            it += 1; sec += ns; cost += std::max(floor_cost, ns);
+        }
+    }
+    out[0] = it / warps; out[1] = sec / it; out[2] = cost / warps; out[3] = gvis / warps; out[4] = lvis / warps;
+    return 0;
+}
