@@ -30,6 +30,7 @@
 
 #include <stdint.h>
 #include <math.h>
+#include <string.h>
 
 #if defined(__CUDACC__)
 #define BH_HD __host__ __device__ __forceinline__
@@ -333,6 +334,104 @@ BH_HD void bh_climb_body(const BhTreeView& t, const BhRoot& root, int i, double 
         carry = s.cnt;
         p = q;
     }
+}
+
+// ---- jitter regime (BH.kt:145-156) ---------------------------------------------------------------
+// A node with half-side h < 1e-3 (depth >= root.levels) that has to push bodies into its children
+// first MUTATES them: x += (LSB(bits(x)) == 0 ? +1e-3 : -1e-3), y += (LSB(bits(y)) == 0 ? -1e-3 :
+// +1e-3); a body shifted out of the child picked for it is silently dropped by the next insert()
+// (BH.kt:126).  Only bodies that share a depth-`levels` cell C (equal Morton keys) are affected, and
+// the outcome depends on their insertion order (list order), so each such cluster is replayed
+// sequentially, in f64, exactly as BHTree.insert / insertIntoChild would run (BH.kt:125-156).
+// Because C's children are narrower than the 1e-3 shift, nothing survives below depth levels+1:
+// a child of C ends up empty, holding one body, or "dead" (subdivided, all four children empty).
+//
+// ord[0..r) = body slots of the cluster (r >= 2); perm[slot] = position in the reference's list.
+// On return x/y hold the mutated coordinates, jflag[slot] bit 0 = 1 for a dropped body (it stays
+// in the sorted order as a zero-mass ghost leaf: invisible to masses and forces), ord[] lists the
+// surviving bodies first, by child digit (the order computeMass sums them in), and
+// jflag[ord[0]] bits 4..7 = mask of dead children (only the debug export shows those).
+BH_HD double bh_jitter_shift(double v, bool plus_if_even) {
+    long long bits;
+#if defined(__CUDA_ARCH__)
+    bits = __double_as_longlong(v);
+#else
+    memcpy(&bits, &v, 8);
+#endif
+    const bool even = (bits & 1LL) == 0LL;
+    return BH_DADD(v, (even == plus_if_even) ? 1e-3 : -1e-3);
+}
+BH_HD bool bh_quad_contains(double cx, double cy, double h, double x, double y) {   // BH.kt:61-62
+    return x >= BH_DSUB(cx, h) && x < BH_DADD(cx, h) && y >= BH_DSUB(cy, h) && y < BH_DADD(cy, h);
+}
+BH_HD void bh_jitter_cluster(const BhRoot& root, uint64_t key, int* ord, int r, const int* __restrict__ perm,
+                             double* x, double* y, int* jflag, int* unsupported, int* n_ghost) {
+    // insertion order = list order: heap-sort the members by perm[]
+    for (int start = r / 2 - 1; start >= 0; --start) {
+        int i = start;
+        for (;;) {
+            int c = 2 * i + 1;
+            if (c >= r) break;
+            if (c + 1 < r && perm[ord[c + 1]] > perm[ord[c]]) ++c;
+            if (perm[ord[c]] <= perm[ord[i]]) break;
+            const int tmp = ord[c]; ord[c] = ord[i]; ord[i] = tmp; i = c;
+        }
+    }
+    for (int end = r - 1; end > 0; --end) {
+        int tmp = ord[0]; ord[0] = ord[end]; ord[end] = tmp;
+        int i = 0;
+        for (;;) {
+            int c = 2 * i + 1;
+            if (c >= end) break;
+            if (c + 1 < end && perm[ord[c + 1]] > perm[ord[c]]) ++c;
+            if (perm[ord[c]] <= perm[ord[i]]) break;
+            tmp = ord[c]; ord[c] = ord[i]; ord[i] = tmp; i = c;
+        }
+    }
+    double cx, cy, h;
+    bh_cell_geometry(root, key, root.levels, &cx, &cy, &h);
+    const double hh = h / 2.0;            // Quad.child, BH.kt:73-80
+    int kbody[4] = {-1, -1, -1, -1};
+    int dead = 0;
+    // insertIntoChild of a DEAD child K (or of K while it subdivides): jitter, pick K's child, insert
+    // there; its containment test cannot pass (K is narrower than the shift) but is made literally.
+    auto sink = [&](int b, double kcx, double kcy) {
+        x[b] = bh_jitter_shift(x[b], true);
+        y[b] = bh_jitter_shift(y[b], false);
+        const double qh = hh / 2.0;
+        const double qcx = (x[b] < kcx) ? BH_DSUB(kcx, qh) : BH_DADD(kcx, qh);
+        const double qcy = (y[b] < kcy) ? BH_DSUB(kcy, qh) : BH_DADD(kcy, qh);
+        if (bh_quad_contains(qcx, qcy, qh, x[b], y[b])) *unsupported = 1;
+    };
+    // insertIntoChild at C (BH.kt:145-156) followed by the child's insert() (BH.kt:125-137)
+    auto place = [&](int b) {
+        x[b] = bh_jitter_shift(x[b], true);
+        y[b] = bh_jitter_shift(y[b], false);
+        const int ix = (x[b] < cx) ? 0 : 1, iy = (y[b] < cy) ? 0 : 2;
+        const int c = ix + iy;
+        const double kcx = ix ? BH_DADD(cx, hh) : BH_DSUB(cx, hh);
+        const double kcy = iy ? BH_DADD(cy, hh) : BH_DSUB(cy, hh);
+        if (!bh_quad_contains(kcx, kcy, hh, x[b], y[b])) return;          // dropped, BH.kt:126
+        if (dead & (1 << c)) { sink(b, kcx, kcy); return; }
+        if (kbody[c] < 0) { kbody[c] = b; return; }                       // empty leaf, BH.kt:127-130
+        const int e = kbody[c];                                           // subdivide, BH.kt:131-136
+        kbody[c] = -1;
+        dead |= 1 << c;
+        sink(e, kcx, kcy);
+        sink(b, kcx, kcy);
+    };
+    place(ord[0]);                        // the resident of C is pushed down first (BH.kt:132-135)
+    for (int k = 1; k < r; ++k) place(ord[k]);
+    // survivors first, by child digit; the dropped bodies keep their relative order behind them
+    int nt = 0;
+    for (int k = 0; k < r; ++k) jflag[ord[k]] = 1;
+    for (int c = 0; c < 4; ++c) if (kbody[c] >= 0) { jflag[kbody[c]] = 0; ++nt; }
+    int w = r - 1;
+    for (int k = r - 1; k >= 0; --k) if (jflag[ord[k]] & 1) ord[w--] = ord[k];   // compact ghosts to the back (stable)
+    w = 0;
+    for (int c = 0; c < 4; ++c) if (kbody[c] >= 0) ord[w++] = kbody[c];
+    jflag[ord[0]] |= dead << 4;
+    *n_ghost = r - nt;
 }
 
 struct BhWalkParams {

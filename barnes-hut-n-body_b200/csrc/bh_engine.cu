@@ -71,6 +71,8 @@ struct bh_engine {
     int *origin = nullptr;           // user index -> index in the list of the last bh_set_bodies
     int *leafpos = nullptr;          // home slot -> preorder position of the body's leaf (-1: not in the tree)
     int *itmp = nullptr, *inv = nullptr, *iscr0 = nullptr, *iscr1 = nullptr, *dead = nullptr;
+    int *jflag = nullptr;            // jitter replay flags per home slot (valid iff jitter_active)
+    bool jitter_active = false;      // the last build replayed jitter clusters
     int *cntI = nullptr, *cntO = nullptr;
     bool perm_identity = true, origin_identity = true;
     bool any_zero_mass = false;      // some body has m == 0 (zero-mass cells are pruned, BH.kt:216)
@@ -138,7 +140,7 @@ struct bh_engine {
     void free_bodies() {
         dev_free(x); dev_free(y); dev_free(vx); dev_free(vy); dev_free(m); dev_free(ax); dev_free(ay); dev_free(dtmp);
         dev_free(perm); dev_free(origin); dev_free(leafpos); dev_free(itmp); dev_free(inv); dev_free(iscr0);
-        dev_free(iscr1); dev_free(dead);
+        dev_free(iscr1); dev_free(dead); dev_free(jflag);
         dev_free(cntI); dev_free(cntO);
         dev_free(keys_a); dev_free(keys_b); dev_free(vals_a); dev_free(vals_b); dev_free(scratch); dev_free(S);
         cap = 0;
@@ -170,7 +172,7 @@ struct bh_engine {
         BH_TRY(dev_alloc(&m, cp)); BH_TRY(dev_alloc(&ax, cp)); BH_TRY(dev_alloc(&ay, cp)); BH_TRY(dev_alloc(&dtmp, cp));
         BH_TRY(dev_alloc(&perm, cp)); BH_TRY(dev_alloc(&origin, cp)); BH_TRY(dev_alloc(&leafpos, cp));
         BH_TRY(dev_alloc(&itmp, cp)); BH_TRY(dev_alloc(&inv, cp)); BH_TRY(dev_alloc(&iscr0, cp)); BH_TRY(dev_alloc(&iscr1, cp));
-        BH_TRY(dev_alloc(&dead, cp));
+        BH_TRY(dev_alloc(&dead, cp)); BH_TRY(dev_alloc(&jflag, cp));
         if (cfg.flags & BH_FLAG_BODY_COUNTS) { BH_TRY(dev_alloc(&cntI, cp)); BH_TRY(dev_alloc(&cntO, cp)); }
         BH_TRY(dev_alloc(&keys_a, cp)); BH_TRY(dev_alloc(&keys_b, cp));
         BH_TRY(dev_alloc(&vals_a, cp)); BH_TRY(dev_alloc(&vals_b, cp));
@@ -317,12 +319,21 @@ struct bh_engine {
         ctr.n_in_tree = n_in; ctr.n_out_of_box = n - n_in; ctr.n_internal = n_internal; ctr.n_cells = M;
         ctr.n_jitter_bodies = sc_host->n_jitter; ctr.max_depth = sc_host->max_depth; ctr.key_levels = root.levels;
         BH_RC(ensure_cells((int64_t)M + 1));   // + the terminal record the walk idles on
+        jitter_active = false;
+        if (sc_host->n_jitter > 0) {
+            // jitter regime (BH.kt:145-156): replay each cluster of equal keys sequentially; this
+            // MUTATES x/y of its bodies exactly like the reference's buildTree() does
+            BH_TRY(cudaMemsetAsync(jflag, 0, (size_t)nn * sizeof(int), st));
+            k_jitter<<<grid_for(n_in, 128), 128, 0, st>>>(keys_sorted, const_cast<int*>(order), n_in, root, perm, x, y, jflag, sc());
+            ctr.kernel_launches += 1;
+            jitter_active = true;
+        }
         if (nn > 0) BH_TRY(cudaMemsetAsync(leafpos, 0xFF, (size_t)nn * sizeof(int), st));   // -1: not in the tree
         if (n_in > 0) {
             BH_TRY(cudaMemsetAsync(arrived, 0, (size_t)M * sizeof(int), st));
             const BhTreeView t = view();
             k_emit<<<grid_for(n_in, 256), 256, 0, st>>>(t, root.levels);
-            k_climb<<<grid_for(n_in, 256), 256, 0, st>>>(t, root, x, y, m, leafpos);
+            k_climb<<<grid_for(n_in, 256), 256, 0, st>>>(t, root, x, y, m, jitter_active ? jflag : nullptr, leafpos);
             ctr.kernel_launches += 2;
         }
         BH_TRY(cudaEventRecord(ev[slot + 1], st));
@@ -398,6 +409,10 @@ struct bh_engine {
         ctr.interactions = (int64_t)sc_host->interactions;
         ctr.opened = (int64_t)sc_host->opened;
         ctr.exact_retests = (int64_t)sc_host->retests;
+        if (jitter_active) {
+            ctr.n_in_tree = n_in - sc_host->n_ghost;
+            if (sc_host->jitter_unsupported) return fail(BH_E_UNSUPPORTED, "jitter regime: a body survived below depth levels+1");
+        }
         ctr.total_interactions = (int64_t)tot_host->interactions;
         ctr.total_opened = (int64_t)tot_host->opened;
         if (comm_pending) {
@@ -703,7 +718,7 @@ int bh_build_tree(bh_engine* e) {
     if (!e) return BH_E_ARG;
     E_TRY(cudaSetDevice(e->device));
     E_RC(e->build());
-    E_TRY(cudaStreamSynchronize(e->st));
+    E_RC(e->finish());
     return BH_OK;
 }
 
@@ -771,7 +786,7 @@ int bh_get_morton(bh_engine* e, uint64_t* key, int32_t* depth, int32_t* order) {
     if (ce == cudaSuccess) {
         // sentinel here is the ABI's UINT64_MAX, not the sortable 1<<2L
         k_keygen<<<grid_for(n, 256), 256, 0, e->st>>>(e->x, e->y, n, e->root, BH_KEY_NOT_IN_TREE, dkey, nullptr);
-        k_leaf_depth<<<grid_for(n, 256), 256, 0, e->st>>>(e->view(), e->leafpos, n, ddepth);
+        k_leaf_depth<<<grid_for(n, 256), 256, 0, e->st>>>(e->view(), e->leafpos, e->jitter_active ? e->jflag : nullptr, n, ddepth);
         k_scatter<uint64_t><<<grid_for(n, 256), 256, 0, e->st>>>(dkey_u, dkey, e->perm, n);
         ce = cudaGetLastError();
         if (ce == cudaSuccess && key) ce = cudaMemcpyAsync(key, dkey_u, (size_t)n * 8, cudaMemcpyDeviceToHost, e->st);
@@ -814,7 +829,15 @@ int bh_get_tree(bh_engine* e, int64_t cap, int64_t* n_cells, double* cx, double*
                 for (size_t i = 0; i < ni; ++i) order[i] = perm[(size_t)order[i]];
             }
         }
-        BhHostTree t{e->root, e->n_in, e->M, keys.data(), order.data(), S.data(), sk.data(), cd.data()};
+        std::vector<int> jf;   // jitter flags per sorted position
+        if (e->jitter_active && ni) {
+            std::vector<int> jh((size_t)e->n), ord_home(ni);
+            E_TRY(cudaMemcpy(jh.data(), e->jflag, (size_t)e->n * 4, cudaMemcpyDeviceToHost));
+            E_TRY(cudaMemcpy(ord_home.data(), e->order, ni * 4, cudaMemcpyDeviceToHost));
+            jf.resize(ni);
+            for (size_t i = 0; i < ni; ++i) jf[i] = jh[(size_t)ord_home[i]];
+        }
+        BhHostTree t{e->root, e->n_in, e->M, keys.data(), order.data(), S.data(), sk.data(), cd.data(), jf.empty() ? nullptr : jf.data()};
         BhCellsOut out;
         out.cap = cap; out.cx = cx; out.cy = cy; out.h = h; out.mass = mass; out.comx = comx; out.comy = comy; out.body = body;
         bh_export_cells(t, out);

@@ -18,6 +18,7 @@ struct BhHostTree {
     const int* S;             // [n_in+1]
     const BhCellS* sk;        // [M] skeletons
     const BhCellD* cd;        // [M] exact f64 records
+    const int* jflag;         // [n_in] jitter replay flags per sorted position, or nullptr
 };
 
 struct BhCellsOut {
@@ -59,9 +60,32 @@ inline void rec(Ctx& c, int p, double cx, double cy, double h) {
     int ch = p + 1;
     const int end = t.sk[p].skip;
     if (d >= t.root.levels) {
-        // jitter-regime cluster (bodies sharing a cell with h < 1e-3): not a reference-shaped
-        // subtree; list its bodies as leaves of child 0's geometry so the export stays total.
-        for (; ch < end; ch = t.sk[ch].skip) rec(c, ch, cx - hh, cy - hh, hh);
+        // jitter-regime cluster (bh_jitter_cluster): C's surviving bodies sit in the child their
+        // (mutated) position selects; a "dead" child is an internal cell with four empty leaves;
+        // dropped bodies (ghost leaves) are not part of the reference's tree
+        const int mask = t.jflag ? (t.jflag[c.first[ch]] >> 4) & 15 : 0;
+        for (int dig = 0; dig < 4; ++dig) {
+            const double ccx = (dig & 1) ? cx + hh : cx - hh;
+            const double ccy = (dig & 2) ? cy + hh : cy - hh;
+            int found = -1;
+            for (int q = ch; q < end; q = t.sk[q].skip) {
+                if (t.jflag && (t.jflag[c.first[q]] & 1)) continue;
+                const int qd = (t.cd[q].comx < cx ? 0 : 1) + (t.cd[q].comy < cy ? 0 : 2);
+                if (qd == dig) { found = q; break; }
+            }
+            if (found >= 0) {
+                c.out.put(ccx, ccy, hh, t.cd[found].mass, t.cd[found].comx, t.cd[found].comy, (int32_t)t.order[c.first[found]]);
+            } else if (mask & (1 << dig)) {
+                const double qh = hh / 2.0;
+                c.out.put(ccx, ccy, hh, 0.0, ccx, ccy, -2);
+                for (int g = 0; g < 4; ++g) {
+                    const double gx = (g & 1) ? ccx + qh : ccx - qh, gy = (g & 2) ? ccy + qh : ccy - qh;
+                    c.out.put(gx, gy, qh, 0.0, gx, gy, -1);
+                }
+            } else {
+                c.out.put(ccx, ccy, hh, 0.0, ccx, ccy, -1);
+            }
+        }
         return;
     }
     const int sh = 2 * (t.root.levels - 1 - d);

@@ -22,7 +22,9 @@ struct DevScalars {           // zeroed at the start of every build
     int max_depth;
     unsigned long long interactions, opened, retests;   // of the evaluation that follows
     unsigned int scan_ticket;
-    unsigned int pad;
+    unsigned int pad;         // always 0: the walk adds it to its base pointer (see bh_walk_body)
+    int n_ghost;              // bodies dropped by the jitter replay (ghost leaves)
+    int jitter_unsupported;   // a jittered body survived below depth levels+1 (cannot happen for h < 1e-3)
 };
 struct DevTotals {            // zeroed by bh_reset_counters only
     unsigned long long interactions, opened, retests, evaluations;
@@ -175,13 +177,15 @@ __global__ void __launch_bounds__(256) k_emit(BhTreeView t, int levels) {
 // preorder position of each body's leaf (leafpos, pre-filled with -1 for bodies not in the tree)
 __global__ void __launch_bounds__(256) k_climb(BhTreeView t, BhRoot root, const double* __restrict__ x,
                                                const double* __restrict__ y, const double* __restrict__ m,
-                                               int* __restrict__ leafpos) {
+                                               const int* __restrict__ jflag, int* __restrict__ leafpos) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= t.n_in) return;
     const int b = t.order[i];
     leafpos[b] = t.S[i + 1] + i;
     if (i == 0) bh_write_terminal_cell(t);
-    bh_climb_body(t, root, i, x[b], y[b], m[b]);
+    // a body dropped by the jitter replay stays as a zero-mass ghost leaf (bh_jitter_cluster)
+    const double mb = (jflag && (jflag[b] & 1)) ? 0.0 : m[b];
+    bh_climb_body(t, root, i, x[b], y[b], mb);
 }
 
 // accumulateForce (BH.kt:215-239) + ax = fx/m (BH.kt:390-391): one thread per target body.
@@ -386,11 +390,29 @@ __global__ void k_positions_f32(const double* __restrict__ x, const double* __re
 }
 
 // depth of each body's leaf (-1: not in the tree), home order
-__global__ void k_leaf_depth(BhTreeView t, const int* __restrict__ leafpos, int n, int* __restrict__ depth) {
+__global__ void k_leaf_depth(BhTreeView t, const int* __restrict__ leafpos, const int* __restrict__ jflag, int n,
+                             int* __restrict__ depth) {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= n) return;
     const int lp = leafpos[b];
-    depth[b] = (lp >= 0) ? t.sk[lp].level : -1;
+    depth[b] = (lp >= 0 && !(jflag && (jflag[b] & 1))) ? t.sk[lp].level : -1;
+}
+
+// Jitter regime (BH.kt:145-156): the thread at the first key of every run of equal keys replays
+// that cluster sequentially (bh_jitter_cluster).  Launched only when the scan found such runs.
+__global__ void __launch_bounds__(128)
+k_jitter(const uint64_t* __restrict__ keys, int* __restrict__ order, int n_in, BhRoot root, const int* __restrict__ perm,
+         double* __restrict__ x, double* __restrict__ y, int* __restrict__ jflag, DevScalars* __restrict__ sc) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_in - 1) return;
+    const uint64_t k = keys[i];
+    if (keys[i + 1] != k || (i > 0 && keys[i - 1] == k)) return;
+    int j = i + 1;
+    while (j + 1 < n_in && keys[j + 1] == k) ++j;
+    int unsupported = 0, ghosts = 0;
+    bh_jitter_cluster(root, k, order + i, j - i + 1, perm, x, y, jflag, &unsupported, &ghosts);
+    if (ghosts) atomicAdd(&sc->n_ghost, ghosts);
+    if (unsupported) atomicExch(&sc->jitter_unsupported, 1);
 }
 
 // ---- permutation helpers (home order <-> user order, re-homing) -----------------------------

@@ -19,6 +19,10 @@ struct Emul {
     std::vector<BhCell> cell;
     std::vector<BhCellD> cd;
     std::vector<BhCellS> sk;
+    std::vector<double> xm, ym;     // coordinates after the jitter replay (BH.kt:145-156 mutates bodies)
+    std::vector<int> jflag;         // per body
+    std::vector<int> jsorted;       // per sorted position (for the export)
+    int n_ghost = 0, unsupported = 0;
     BhTreeView view() {
         BhTreeView t{};
         t.keys = keys.data(); t.order = order.data(); t.S = S.data();
@@ -49,11 +53,32 @@ static void build(Emul& e, int n, const double* x, const double* y, const double
         e.S[i + 1] = e.S[i] + (dnext > dprev ? dnext - dprev : 0);
     }
     e.M = e.n_in + e.S[e.n_in];
+    // jitter regime: replay every run of equal keys (the engine does this in k_jitter)
+    e.xm.assign(x, x + n); e.ym.assign(y, y + n);
+    e.jflag.assign(n, 0);
+    {
+        std::vector<int> ident(n);
+        std::iota(ident.begin(), ident.end(), 0);
+        for (int i = 0; i + 1 < e.n_in;) {
+            int j = i;
+            while (j + 1 < e.n_in && e.keys[j + 1] == e.keys[i]) ++j;
+            if (j > i) {
+                int un = 0, gh = 0;
+                bh_jitter_cluster(e.root, e.keys[i], e.order.data() + i, j - i + 1, ident.data(), e.xm.data(), e.ym.data(),
+                                  e.jflag.data(), &un, &gh);
+                e.n_ghost += gh; e.unsupported |= un;
+            }
+            i = j + 1;
+        }
+    }
+    x = e.xm.data(); y = e.ym.data();
+    e.jsorted.resize(e.n_in);
+    for (int i = 0; i < e.n_in; ++i) e.jsorted[i] = e.jflag[e.order[i]];
     e.arrived.assign(e.M, 0);
     e.cell.assign(e.M, BhCell{}); e.cd.assign(e.M, BhCellD{}); e.sk.assign(e.M, BhCellS{});
     BhTreeView t = e.view();
     for (int i = 0; i < e.n_in; ++i) bh_emit_body(t, e.root.levels, i);
-    for (int i = 0; i < e.n_in; ++i) { const int b = e.order[i]; bh_climb_body(t, e.root, i, x[b], y[b], m[b]); }
+    for (int i = 0; i < e.n_in; ++i) { const int b = e.order[i]; bh_climb_body(t, e.root, i, x[b], y[b], (e.jflag[b] & 1) ? 0.0 : m[b]); }
 }
 
 extern "C" {
@@ -66,6 +91,7 @@ int bh_emul_accelerations(int n, const double* x, const double* y, const double*
                           uint64_t* key_out, int32_t* depth_out, int32_t* order_out, int64_t* stats) {
     Emul e;
     build(e, n, x, y, m, rcx, rcy, rhalf);
+    x = e.xm.data(); y = e.ym.data();
     BhTreeView t = e.view();
     const BhWalkParams w = bh_walk_params(theta, soft2, rhalf);
     int64_t tI = 0, tO = 0, tR = 0;
@@ -83,9 +109,9 @@ int bh_emul_accelerations(int n, const double* x, const double* y, const double*
         if (key_out) key_out[b] = e.key_by_body[b];
         if (depth_out) depth_out[b] = -1;
     }
-    for (int i = 0; i < e.n_in; ++i) if (depth_out) depth_out[e.order[i]] = e.sk[e.S[i + 1] + i].level;
+    for (int i = 0; i < e.n_in; ++i) if (depth_out && !(e.jflag[e.order[i]] & 1)) depth_out[e.order[i]] = e.sk[e.S[i + 1] + i].level;
     if (order_out) std::memcpy(order_out, e.order.data(), sizeof(int) * (size_t)n);
-    if (stats) { stats[0] = e.n_in; stats[1] = e.M; stats[2] = e.S[e.n_in]; stats[3] = tI; stats[4] = tO; stats[5] = tR; }
+    if (stats) { stats[0] = e.n_in - e.n_ghost; stats[1] = e.M; stats[2] = e.S[e.n_in]; stats[3] = tI; stats[4] = tO; stats[5] = tR; }
     return 0;
 }
 
@@ -95,11 +121,22 @@ int bh_emul_tree(int n, const double* x, const double* y, const double* m, doubl
                  double* comy, int32_t* body) {
     Emul e;
     build(e, n, x, y, m, rcx, rcy, rhalf);
-    BhHostTree t{e.root, e.n_in, e.M, e.keys.data(), e.order.data(), e.S.data(), e.sk.data(), e.cd.data()};
+    BhHostTree t{e.root, e.n_in, e.M, e.keys.data(), e.order.data(), e.S.data(), e.sk.data(), e.cd.data(), e.jsorted.data()};
     BhCellsOut out;
     out.cap = cap; out.cx = cx; out.cy = cy; out.h = h; out.mass = mass; out.comx = comx; out.comy = comy; out.body = body;
     bh_export_cells(t, out);
     if (n_cells) *n_cells = out.count;
+    return 0;
+}
+
+// coordinates after one buildTree() (the jitter replay mutates bodies, BH.kt:145-156)
+int bh_emul_positions_after_build(int n, const double* x, const double* y, const double* m, double rcx, double rcy,
+                                  double rhalf, double* xout, double* yout, int64_t* stats /* n_ghost, unsupported */) {
+    Emul e;
+    build(e, n, x, y, m, rcx, rcy, rhalf);
+    std::memcpy(xout, e.xm.data(), sizeof(double) * (size_t)n);
+    std::memcpy(yout, e.ym.data(), sizeof(double) * (size_t)n);
+    if (stats) { stats[0] = e.n_ghost; stats[1] = e.unsupported; }
     return 0;
 }
 

@@ -107,3 +107,59 @@ def test_insertion_order_invariance(oracle_lib):
     b = make_engine(oracle_lib, tuple(v[perm] for v in s)).tree()
     for q in ("cx", "cy", "h", "mass"):
         assert (a[q] == b[q]).all()
+
+
+# ---- jitter regime (BarnesHutAlg.kt:145-156) ---------------------------------------------------
+def _jitter_scenes():
+    """Bodies that share a cell with h < 1e-3 (depth 21 of the default root, side 1.146e-3):
+    coincident pairs, near-coincident pairs/triples/quads in every mantissa-LSB combination,
+    clusters whose members are far apart in list order, a cluster with a zero-mass body."""
+    rng = np.random.default_rng(77)
+    base = scenes.make_uniform_random(1500, 0.5, seed=21)
+    x, y, vx, vy, m = [a.copy() for a in base]
+    def put(idx, x0, y0, offs):
+        for k, (dx, dy) in zip(idx, offs):
+            x[k], y[k] = x0 + dx, y0 + dy
+    put([3, 4], 100.25, 100.25, [(0, 0), (0, 0)])                                   # exactly coincident
+    put([10, 900], 333.333, 250.5, [(0, 0), (1e-5, -2e-5)])                         # far apart in list order
+    put([20, 21, 22], 1500.1, 400.2, [(0, 0), (3e-5, 1e-5), (-2e-5, 4e-5)])         # triple
+    put([30, 31, 32, 33], 700.7, 123.4, [(0, 0), (1e-4, 0), (0, 1e-4), (1e-4, 1e-4)])
+    for q in range(40):                                                              # random LSB parities
+        i0 = 100 + 3 * q
+        cx0, cy0 = rng.uniform(50, 2350), rng.uniform(50, 750)
+        put([i0, i0 + 1, i0 + 2], cx0, cy0, rng.uniform(-2e-4, 2e-4, (3, 2)))
+    put([400, 401, 402, 403, 404, 405, 406], 1200.0, 400.0, rng.uniform(-1e-4, 1e-4, (7, 2)))   # centre of the box
+    m[401] = 0.0
+    return [("mixed clusters", (x, y, vx, vy, m))]
+
+
+@pytest.mark.parametrize("name,scene", _jitter_scenes(), ids=[s[0] for s in _jitter_scenes()])
+@pytest.mark.parametrize("theta", [0.5, 0.0])
+def test_jitter_regime_matches_oracle(oracle_lib, emul_lib, name, scene, theta):
+    o = make_engine(oracle_lib, scene, 2400, 800, flags=1, theta=theta)
+    p = o.params
+    ax, ay = o.compute_accelerations()        # buildTree() mutates the clustered bodies
+    ci, co = o.body_counts()
+    depth, path = leaf_paths(oracle_lib, o)
+    ox, oy, *_ = o.get_bodies()
+    assert (ox != scene[0]).sum() > 50        # the regime was really exercised
+    assert (depth < 0).sum() > 10             # ... and dropped bodies exist
+    x, y, vx, vy, m = (np.ascontiguousarray(a, np.float64) for a in scene)
+    n = len(x)
+    gx, gy, st = np.empty(n), np.empty(n), np.zeros(2, np.int64)
+    emul_lib.bh_emul_positions_after_build(n, _dp(x), _dp(y), _dp(m), C.c_double(p.root_cx), C.c_double(p.root_cy),
+                                           C.c_double(p.root_half), _dp(gx), _dp(gy), st.ctypes.data_as(I64))
+    assert st[1] == 0
+    assert (gx == ox).all() and (gy == oy).all()          # mutated coordinates, bit-exact
+    assert st[0] == int((depth < 0).sum())                # the same bodies were dropped
+    g = emul_acc(emul_lib, scene, p, theta)
+    assert (g["depth"] == depth).all()
+    assert (g["ci"] == ci).all() and (g["co"] == co).all()
+    ok = np.isfinite(ax)
+    s = acc_errors(ax[ok], ay[ok], g["ax"][ok], g["ay"][ok])
+    assert s["normwise"] < 1e-6, s
+    to = o.tree()
+    k, tg = emul_tree(emul_lib, scene, p, len(to["cx"]))
+    assert k == len(to["cx"])
+    for q in to:
+        assert (tg[q] == to[q]).all(), q
