@@ -307,11 +307,9 @@ BH_HD void bh_write_cell(const BhTreeView& t, int p, double cx, double cy, doubl
 // at each parent it adds the body count of the finished child (one acq_rel atomic) and
 // continues only if that completed the parent — the last arriver sums the children in
 // child order 0..3 (= preorder order) with the reference's exact f64 expression order.
-BH_HD void bh_climb_body(const BhTreeView& t, const BhRoot& root, int i, double x, double y, double m) {
-    int p = t.S[i + 1] + i;
-    BhCellS s = t.sk[p];
-    bh_write_cell(t, p, x, y, m, s.skip, s.level, true, root.half);
-    int carry = 1;
+// Continues the climb above a finished cell whose skeleton is `s` and which holds `carry` bodies;
+// `key` = Morton key of any body below it (cell geometry of a zero-mass ancestor, BH.kt:197-200).
+BH_HD void bh_climb_from(const BhTreeView& t, const BhRoot& root, uint64_t key, BhCellS s, int carry) {
     for (;;) {
         const int q = s.parent;
         if (q < 0) break;
@@ -329,11 +327,16 @@ BH_HD void bh_climb_body(const BhTreeView& t, const BhRoot& root, int i, double 
         }
         double cx, cy;
         if (mSum > 0.0) { cx = BH_DDIV(sx, mSum); cy = BH_DDIV(sy, mSum); }   // BH.kt:194-196
-        else { double h; bh_cell_geometry(root, t.keys[i], s.level, &cx, &cy, &h); }  // BH.kt:197-200
+        else { double h; bh_cell_geometry(root, key, s.level, &cx, &cy, &h); }  // BH.kt:197-200
         bh_write_cell(t, q, cx, cy, mSum, s.skip, s.level, false, root.half);
         carry = s.cnt;
-        p = q;
     }
+}
+BH_HD void bh_climb_body(const BhTreeView& t, const BhRoot& root, int i, double x, double y, double m) {
+    const int p = t.S[i + 1] + i;
+    const BhCellS s = t.sk[p];
+    bh_write_cell(t, p, x, y, m, s.skip, s.level, true, root.half);
+    bh_climb_from(t, root, t.keys[i], s, 1);
 }
 
 // ---- jitter regime (BH.kt:145-156) ---------------------------------------------------------------

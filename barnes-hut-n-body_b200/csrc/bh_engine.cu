@@ -60,7 +60,15 @@ struct bh_engine {
     bh_params par{};
     int device = 0, num_sms = 148;
     cudaStream_t st = nullptr;
-    cudaEvent_t ev[16]{};   // [0..3] evaluation A, [4..7] evaluation B, [8..9] step, [10..11] call, [12..13] comm
+    // CUDA-event timing slots: a ring, so that a multi-step bh_step never waits for the device just
+    // to read its timers.  Per slot: [0..3] evaluation A, [4..7] evaluation B, [8..9] step,
+    // [12..13] exchange, [14..15] merge rule.  `ev` = the slot in use; call_ev = whole call.
+    static constexpr int EV_RING = 4;
+    struct EvSlot { cudaEvent_t e[16]{}; bool used = false, has_comm = false, has_merge = false; };
+    EvSlot ring[EV_RING];
+    EvSlot* cur = &ring[0];
+    cudaEvent_t* ev = ring[0].e;
+    cudaEvent_t call_ev[2]{};
     std::string err;
 
     // body state, f64 SoA in HOME order
@@ -260,10 +268,9 @@ struct bh_engine {
         if (rc == bhcomm::kSuccess) rc = rc2;
         if (rc != bhcomm::kSuccess) return nccl_fail(rc, "ncclAllGather");
         BH_TRY(cudaEventRecord(ev[13], st));
-        comm_pending = true;
+        cur->has_comm = true;
         return BH_OK;
     }
-    bool comm_pending = false;
     // every rank needs every body's velocity (re-homing, removal of merged bodies, read-back)
     int sync_velocities() {
         if (vel_valid || world <= 1) { vel_valid = true; return BH_OK; }
@@ -415,11 +422,6 @@ struct bh_engine {
         }
         ctr.total_interactions = (int64_t)tot_host->interactions;
         ctr.total_opened = (int64_t)tot_host->opened;
-        if (comm_pending) {
-            float c = 0.f;
-            if (cudaEventElapsedTime(&c, ev[12], ev[13]) == cudaSuccess) ctr.ms_comm += c;
-            comm_pending = false;
-        }
         return BH_OK;
     }
     // events of evaluate(slot); call after a sync.  Returns build+walk ms.
@@ -481,27 +483,47 @@ struct bh_engine {
     int merge_rule();
     int merge_done();
     int run_steps(int nsteps);
+    void collect(EvSlot& sl);
 };
 
 #include "bh_merge.cuh"
 
+// fold the timers of a finished step slot into the counters (waits for that step only)
+void bh_engine::collect(EvSlot& sl) {
+    if (!sl.used) return;
+    cudaEventSynchronize(sl.e[9]);
+    cudaEvent_t* keep = ev;
+    ev = sl.e;
+    const float phases = add_phase_times(0) + add_phase_times(4);
+    float total = 0.f, c = 0.f, mg = 0.f;
+    // kick/drift (+ exchange, merge) = whole step minus the build and walk phases
+    if (cudaEventElapsedTime(&total, ev[8], ev[9]) == cudaSuccess && total > phases) ctr.ms_integrate += total - phases;
+    if (sl.has_comm && cudaEventElapsedTime(&c, ev[12], ev[13]) == cudaSuccess) ctr.ms_comm += c;
+    if (sl.has_merge && cudaEventElapsedTime(&mg, ev[14], ev[15]) == cudaSuccess) ctr.ms_merge += mg;
+    sl.used = sl.has_comm = sl.has_merge = false;
+    ev = keep;
+}
+
 int bh_engine::run_steps(int nsteps) {
-    BH_TRY(cudaEventRecord(ev[10], st));
-    for (int s = 0; s < nsteps; ++s) {
+    BH_TRY(cudaEventRecord(call_ev[0], st));
+    int rc = BH_OK;
+    for (int s = 0; s < nsteps && rc == BH_OK; ++s) {
+        EvSlot& sl = ring[s % EV_RING];
+        collect(sl);
+        cur = &sl; ev = sl.e;
+        sl.used = true;
         BH_TRY(cudaEventRecord(ev[8], st));
-        const int rc = step_once();
-        if (rc != BH_OK) { phase = 0; return rc; }
+        rc = step_once();
+        if (rc != BH_OK) { phase = 0; sl.used = false; break; }
         BH_TRY(cudaEventRecord(ev[9], st));
-        BH_RC(finish());
-        const float phases = add_phase_times(0) + add_phase_times(4);
-        float total = 0.f;
-        // kick/drift (+ exchange, merge) = whole step minus the build and walk phases
-        if (cudaEventElapsedTime(&total, ev[8], ev[9]) == cudaSuccess && total > phases) ctr.ms_integrate += total - phases;
     }
-    BH_TRY(cudaEventRecord(ev[11], st));
+    for (auto& sl : ring) collect(sl);
+    cur = &ring[0]; ev = ring[0].e;
+    if (rc != BH_OK) return rc;
+    BH_TRY(cudaEventRecord(call_ev[1], st));
     BH_RC(finish());
     float call_ms = 0.f;
-    if (cudaEventElapsedTime(&call_ms, ev[10], ev[11]) == cudaSuccess) ctr.ms_step_call = call_ms;
+    if (cudaEventElapsedTime(&call_ms, call_ev[0], call_ev[1]) == cudaSuccess) ctr.ms_step_call = call_ms;
     return BH_OK;
 }
 
@@ -534,7 +556,8 @@ int bh_create(const bh_config* cfg, bh_engine** out) {
     if (const char* s = getenv("BH_WALK_GROUP_MIN_WAVES")) e->walk_group_min_waves = atoi(s);
     cudaError_t ce = cudaSetDevice(e->device);
     if (ce == cudaSuccess) ce = cudaStreamCreateWithFlags(&e->st, cudaStreamNonBlocking);
-    for (int k = 0; k < 16 && ce == cudaSuccess; ++k) ce = cudaEventCreate(&e->ev[k]);
+    for (auto& sl : e->ring) for (int k = 0; k < 16 && ce == cudaSuccess; ++k) ce = cudaEventCreate(&sl.e[k]);
+    for (int k = 0; k < 2 && ce == cudaSuccess; ++k) ce = cudaEventCreate(&e->call_ev[k]);
     if (ce == cudaSuccess) ce = cudaMallocHost((void**)&e->sc_host, sizeof(DevScalars));
     if (ce == cudaSuccess) ce = cudaMallocHost((void**)&e->tot_host, sizeof(DevTotals));
     if (ce == cudaSuccess) ce = cudaMallocHost((void**)&e->hflags, HF_COUNT * sizeof(int));
@@ -569,7 +592,8 @@ void bh_destroy(bh_engine* e) {
     if (e->sc_host) cudaFreeHost(e->sc_host);
     if (e->tot_host) cudaFreeHost(e->tot_host);
     if (e->hflags) cudaFreeHost(e->hflags);
-    for (auto& ev : e->ev) if (ev) cudaEventDestroy(ev);
+    for (auto& sl : e->ring) for (auto& ev : sl.e) if (ev) cudaEventDestroy(ev);
+    for (auto& ev : e->call_ev) if (ev) cudaEventDestroy(ev);
     if (e->st) cudaStreamDestroy(e->st);
     delete e;
 }
@@ -711,6 +735,9 @@ int bh_step_finish(bh_engine* e) {
     E_TRY(cudaSetDevice(e->device));
     E_RC(e->step_finish());
     E_TRY(cudaStreamSynchronize(e->st));
+    float mg = 0.f;
+    if (e->cur->has_merge && cudaEventElapsedTime(&mg, e->ev[14], e->ev[15]) == cudaSuccess) e->ctr.ms_merge += mg;
+    e->cur->has_merge = false;
     return BH_OK;
 }
 

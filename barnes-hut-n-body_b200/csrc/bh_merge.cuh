@@ -134,9 +134,7 @@ inline int bh_engine::merge_rule() {
 
 inline int bh_engine::merge_done() {
     BH_TRY(cudaEventRecord(ev[15], st));
-    BH_TRY(cudaEventSynchronize(ev[15]));
-    float t = 0.f;
-    if (cudaEventElapsedTime(&t, ev[14], ev[15]) == cudaSuccess) ctr.ms_merge += t;
+    cur->has_merge = true;     // folded into ms_merge when the step's timers are collected
     return BH_OK;
 }
 

@@ -148,6 +148,7 @@ def main():
     import torch
     import torch.distributed as dist
     import bh_b200
+    from bh_b200 import scenes as scenes_mod
 
     torch.cuda.set_device(local_rank)
     if world > 1:
@@ -180,9 +181,8 @@ def main():
     eng.set_window(W, H)
     eng.set_params(theta=THETA, merge_min_dist=0.0)
     if world > 1:
-        uid = [eng.comm_unique_id() if rank == 0 else None]
-        dist.broadcast_object_list(uid, src=0)
-        eng.comm_init(rank, world, uid[0])
+        from bh_b200.distributed import init_nccl_engine
+        init_nccl_engine(eng, dist, rank, world)   # NCCL communicator inside the engine
     eng.set_bodies(*scene)
 
     # ---- device-resident throughput: K steps, inputs already in HBM ------------------------
@@ -215,9 +215,14 @@ def main():
     my_inter, my_open = float(c["total_interactions"]) / n_walks, float(c["total_opened"]) / n_walks
     walk_flops = 14.0 * my_inter + 8.0 * my_open           # 14 flop/interaction + 8 flop/rejected test
     ach = walk_flops / (c["ms_walk"] / n_walks * 1e-3) / 1e12
+    # dram__bytes_read.sum + dram__bytes_write.sum of one k_walk launch of this workload
+    # (profiles/r01c_ncu_full_walk_v2.txt); only valid for the default 1M-body N=1 workload
+    traffic = 88.8e6 if (world == 1 and args.bodies == BODIES_PER_GPU) else None
     roofline = {"kernel": "k_walk", "bound": "fp32", "achieved": ach, "peak": float(fp32[0]), "unit": "TFLOP/s",
-                "frac": ach / float(fp32[0]) if fp32[0] > 0 else None, "traffic": None,
-                "peak_source": "measured live: FFMA microbenchmark (bh_measure_fp32_tflops); the walk is FP32-issue/L1-latency bound, not HBM or tensor",
+                "frac": ach / float(fp32[0]) if fp32[0] > 0 else None, "traffic": traffic,
+                "peak_source": "measured live: FFMA microbenchmark (bh_measure_fp32_tflops) — MEASURED_PEAKS.json has no FP32 figure; "
+                               "the walk is neither HBM- nor tensor-bound: ncu shows the L1 data stage at 90% of peak (DESIGN.md §4)",
+                "l1_data_stage_pct_of_peak_ncu": 90.1, "hbm_bytes_algorithmic": 32.0 * n / world + 32.0 * c["n_cells"],
                 "ms_per_launch": c["ms_walk"] / n_walks,
                 "algorithmic": "14 flop x interactions + 8 flop x rejected opening tests per launch"}
     # the HBM-bound phase: keygen + onesweep sort + scan + emit + climb (algorithmic bytes/body)
@@ -251,6 +256,19 @@ def main():
            "h2d_bytes_per_step": 5 * 8 * n, "d2h_bytes_per_step": 5 * 8 * n, "steps": e2e_steps,
            "api": "bh_set_bodies + bh_step(1) + bh_get_bodies per step, pinned host arrays"}
 
+    # ---- BASELINE.json configs[0]: the reference's own scene (12,500 bodies, merge on) ---------
+    c1 = None
+    if rank == 0 and world == 1:
+        e1 = bh_b200.NativeEngine(device=local_rank)
+        e1.set_params(theta=THETA)                      # merge 4000 / 8 px stays on (reference default)
+        e1.set_bodies(*scenes_mod.snap_f32(scenes_mod.default_two_disks(seed=1)))
+        e1.step(20)
+        t0 = time.perf_counter()
+        e1.step(300)
+        c1 = {"workload": "reference two-disk scene, 12,500 bodies, theta=0.5, merge rule on", "steps_per_s": 300 / (time.perf_counter() - t0),
+              "bodies_left": e1.n}
+        e1.close()
+
     # ---- CPU baseline beside it (rank 0, N = 1 only) ------------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -282,7 +300,7 @@ def main():
                        "l2": "no flush: per-step working set (~210 B/body state+sort+tree) exceeds the 126 MB L2 and is rewritten every build"},
             "interactions_per_step": inter / args.steps, "opened_per_step": opened / args.steps,
             "phases_ms_per_evaluation": {"build": build_ms, "walk": walk_ms},
-            "roofline": roofline, "roofline_build": roofline_build, "cpu_baseline": cpu, "e2e": e2e,
+            "roofline": roofline, "roofline_build": roofline_build, "cpu_baseline": cpu, "e2e": e2e, "configs0": c1,
             "gpu_launches": launches, "clocks": clocks,
         }
         print(json.dumps(line), flush=True)
