@@ -25,6 +25,7 @@ _ERR_NAMES = {
 }
 
 BH_FLAG_BODY_COUNTS = 1
+BH_FLAG_REUSE_ACC = 2
 BH_COMM_ID_BYTES = 128
 BH_FIELD_POS = 0
 BH_FIELD_VEL = 1

@@ -130,6 +130,8 @@ struct bh_engine {
     bhcomm::Comm comm = nullptr;
     bool vel_valid = true;           // velocities of ALL bodies are current on this rank
     int phase = 0;                   // 0 idle, 1 after step_begin, 2 after step_end
+    bool acc_valid = false;          // ax/ay of this rank's slice = a(current positions, current params)
+    bh_params acc_par{};             // parameters acc_valid refers to
 
     bh_counters ctr{};
 
@@ -348,7 +350,7 @@ struct bh_engine {
         tree_valid = true;
         return BH_OK;
     }
-    int64_t ctr_rehomes = 0;
+    int64_t ctr_rehomes = 0, ctr_reused = 0;
     int walk_group_min_waves = 0;   // BH_WALK_GROUP_MIN_WAVES > 0: group walk from this many waves of 128-thread blocks per SM
 
     int sort_pairs(int nn, int key_bits) {
@@ -447,7 +449,17 @@ struct bh_engine {
         const double dt = par.dt, dtHalf = par.dt * 0.5;   // BH.kt:412
         int64_t lo, hi;
         my_slice(&lo, &hi);
-        BH_RC(evaluate(0, lo, hi));
+        const bool reuse = (cfg.flags & BH_FLAG_REUSE_ACC) && acc_valid && !rehome_due && acc_par.theta == par.theta &&
+                           acc_par.G == par.G && acc_par.soft2 == par.soft2 && acc_par.root_cx == par.root_cx &&
+                           acc_par.root_cy == par.root_cy && acc_par.root_half == par.root_half;
+        if (reuse) {   // a(t) is the a(t+dt) the previous step ended with: same positions, masses and parameters
+            BH_TRY(cudaEventRecord(ev[0], st)); BH_TRY(cudaEventRecord(ev[1], st));
+            BH_TRY(cudaEventRecord(ev[2], st)); BH_TRY(cudaEventRecord(ev[3], st));
+            ctr_reused++;
+        } else {
+            BH_RC(evaluate(0, lo, hi));
+        }
+        acc_valid = false;
         BH_RC(kick(lo, hi, dtHalf, dt, 1));
         if (world > 1) vel_valid = false;
         phase = 1;
@@ -460,6 +472,8 @@ struct bh_engine {
         my_slice(&lo, &hi);
         BH_RC(evaluate(4, lo, hi));
         BH_RC(kick(lo, hi, dtHalf, dt, 0));
+        acc_valid = !jitter_active;      // a jittering build mutated positions: the next build will again
+        acc_par = par;
         phase = 2;
         return BH_OK;
     }
@@ -657,6 +671,7 @@ int bh_set_bodies(bh_engine* e, int64_t n, const double* x, const double* y, con
     e->tree_valid = false;
     e->heavies_valid = false;
     e->vel_valid = true;
+    e->acc_valid = false;
     return BH_OK;
 }
 
@@ -752,6 +767,7 @@ int bh_build_tree(bh_engine* e) {
 int bh_compute_accelerations(bh_engine* e, double* ax, double* ay) {
     if (!e) return BH_E_ARG;
     E_TRY(cudaSetDevice(e->device));
+    e->acc_valid = false;
     E_RC(e->evaluate(0, 0, e->n));
     E_RC(e->finish());
     e->add_phase_times(0);
@@ -980,7 +996,7 @@ int bh_import_slices(bh_engine* e, int32_t field, int64_t n, const double* a, co
     }
     E_TRY(cudaStreamSynchronize(e->st));
     if (field == BH_FIELD_VEL) e->vel_valid = true;
-    else e->tree_valid = false;
+    else { e->tree_valid = false; e->acc_valid = false; }
     return BH_OK;
 }
 

@@ -83,6 +83,7 @@ inline int bh_engine::merge_rule() {
     const uint32_t* sslot = where ? vals_b : vals_a;
     ctr.kernel_launches += 2 + (32 + kb + 7) / 8;
     BH_TRY(cudaMemsetAsync(dead, 0, (size_t)nn * sizeof(int), st));
+    acc_valid = false;   // masses change
     k_merge_apply<<<1, 32, 0, st>>>(skeys, sslot, cand_home, (int)n_cand, heavy, m, dead, dflags + HF_N_DEAD);
     ctr.kernel_launches += 1;
     BH_TRY(cudaMemcpyAsync(hflags + HF_N_DEAD, dflags + HF_N_DEAD, sizeof(int), cudaMemcpyDeviceToHost, st));

@@ -43,6 +43,11 @@ extern "C" {
 
 /* bh_config.flags */
 #define BH_FLAG_BODY_COUNTS  1u  /* keep per-body interaction / opened-cell counts  */
+#define BH_FLAG_REUSE_ACC    2u  /* CUDA engine: step n+1 starts from the accelerations a(t+dt)
+                                  * step n ended with instead of rebuilding and re-walking the
+                                  * unchanged positions (BarnesHutAlg.kt:407-408 recomputes them).
+                                  * Result-identical; automatically suspended after anything that
+                                  * changes the inputs (set_bodies, Config, merge, jitter).       */
 
 typedef struct bh_engine bh_engine;
 

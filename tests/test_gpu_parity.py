@@ -348,3 +348,29 @@ def test_jitter_regime_matches_oracle(oracle_lib, cuda_lib):
     ok = np.isfinite(so[0])
     d = np.hypot(so[0] - sg[0], so[1] - sg[1])[ok]
     assert np.isfinite(sg[0][ok]).all() and d.max() < 2e-2 and np.median(d) < 1e-6
+
+
+def test_acceleration_reuse_is_result_identical(cuda_lib):
+    """BH_FLAG_REUSE_ACC: step n+1 starts from the a(t+dt) step n ended with (the reference
+    recomputes it from unchanged positions, BH.kt:407-408).  Bit-identical state, also across
+    Config changes, merges and resetBodies, with about half the evaluations."""
+    import bh_b200
+    scene = _merge_scene(seed=51, n1=2500, n2=700)
+    engines = []
+    for flags in (0, bh_b200.BH_FLAG_REUSE_ACC):
+        e = bh_b200.NativeEngine(lib=cuda_lib, flags=flags)
+        e.set_params(theta=0.5, merge_min_dist=8.0)
+        e.set_bodies(*scene)
+        e.step(5)
+        e.set_params(theta=0.35)                # Z key between frames
+        e.step(3)
+        e.set_params(dt=-0.002, G=75.0)         # O / K keys
+        e.step(3)
+        e.set_bodies(*e.get_bodies())           # resetBodies
+        e.step(2)
+        engines.append(e)
+    a, b = engines[0].get_bodies(), engines[1].get_bodies()
+    for u, v in zip(a, b):
+        assert u.shape == v.shape and (u == v).all()
+    assert engines[0].counters()["total_merged"] == engines[1].counters()["total_merged"] > 0
+    assert engines[1].counters()["total_evaluations"] < engines[0].counters()["total_evaluations"]
