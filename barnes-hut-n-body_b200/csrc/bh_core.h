@@ -103,6 +103,60 @@ BH_HD uint64_t bh_morton_key(const BhRoot& r, double x, double y) {
     return key;
 }
 
+// Closed form of the same key.  When every cell boundary x0 + k*w (w = 2*half/2^levels) of the
+// root box is exactly representable in binary64 (bh_grid_is_exact: true for the reference's
+// half-integer root boxes), the centres Quad.child builds by repeated +-h/2 are exact, so the
+// descent's comparisons locate x on that exact grid: the column index is floor((x-x0)/w) in exact
+// arithmetic.  A floating-point estimate is corrected against the exact boundaries (at most one
+// step), then the two indices are bit-interleaved (x = low bit, y = high bit of each digit).
+struct BhGrid { double x0, y0, w, inv_w; int exact; };
+
+BH_HD bool bh_is_multiple_of_pow2(double v, int e) {   // v is an integer multiple of 2^e
+    const double s = ldexp(v, -e);
+    return s == floor(s) && fabs(s) < 9007199254740992.0;
+}
+BH_HD BhGrid bh_make_grid(const BhRoot& r) {
+    BhGrid g;
+    g.x0 = BH_DSUB(r.cx, r.half); g.y0 = BH_DSUB(r.cy, r.half);
+    g.w = ldexp(r.half, 1 - r.levels);
+    g.inv_w = 1.0 / g.w;
+    // quantum of every centre / boundary: half * 2^-levels; all of cx, cy, half must be multiples of
+    // a power of two 2^e with (|coordinate| + 2*half) / 2^(e - levels) < 2^52
+    int ok = 0;
+    for (int e = 0; e >= -12 && !ok; --e) {
+        if (bh_is_multiple_of_pow2(r.cx, e) && bh_is_multiple_of_pow2(r.cy, e) && bh_is_multiple_of_pow2(r.half, e)) {
+            const double span = fmax(fabs(r.cx), fabs(r.cy)) + 2.0 * r.half;
+            ok = ldexp(span, r.levels - e + 1) < 4503599627370496.0;
+            break;
+        }
+    }
+    g.exact = ok && r.levels >= 1 && r.levels <= 31;
+    return g;
+}
+BH_HD uint32_t bh_grid_index(double v, double v0, double w, double inv_w, int levels) {
+    const double nmax = (double)((1u << levels) - 1u);
+    double k = floor(BH_DMUL(BH_DSUB(v, v0), inv_w));
+    k = k < 0.0 ? 0.0 : (k > nmax ? nmax : k);
+    // exact boundaries b(k) = v0 + k*w (representable by construction)
+    while (k > 0.0 && v < BH_DADD(v0, BH_DMUL(k, w))) k -= 1.0;
+    while (k < nmax && v >= BH_DADD(v0, BH_DMUL(k + 1.0, w))) k += 1.0;
+    return (uint32_t)k;
+}
+BH_HD uint64_t bh_spread_bits(uint32_t v) {   // bit i -> bit 2i
+    uint64_t x = v;
+    x = (x | (x << 16)) & 0x0000FFFF0000FFFFull;
+    x = (x | (x << 8)) & 0x00FF00FF00FF00FFull;
+    x = (x | (x << 4)) & 0x0F0F0F0F0F0F0F0Full;
+    x = (x | (x << 2)) & 0x3333333333333333ull;
+    x = (x | (x << 1)) & 0x5555555555555555ull;
+    return x;
+}
+BH_HD uint64_t bh_morton_key_grid(const BhGrid& g, int levels, double x, double y) {
+    const uint32_t ix = bh_grid_index(x, g.x0, g.w, g.inv_w, levels);
+    const uint32_t iy = bh_grid_index(y, g.y0, g.w, g.inv_w, levels);
+    return bh_spread_bits(ix) | (bh_spread_bits(iy) << 1);
+}
+
 // Geometry of the depth-d cell on the path `key` (same arithmetic as Quad.child).
 BH_HD void bh_cell_geometry(const BhRoot& r, uint64_t key, int d, double* ocx, double* ocy, double* oh) {
     double cx = r.cx, cy = r.cy, h = r.half;

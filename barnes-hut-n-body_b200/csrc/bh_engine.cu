@@ -299,7 +299,7 @@ struct bh_engine {
         n_in = 0; n_internal = 0; M = 0;
         if (nn > 0) {
             const uint64_t sentinel = 1ull << (2 * root.levels);
-            k_keygen<<<grid_for(nn, 256), 256, 0, st>>>(x, y, nn, root, sentinel, keys_a, sc());
+            k_keygen<<<std::min(grid_for(nn, 256), num_sms * 16), 256, 0, st>>>(x, y, nn, root, bh_make_grid(root), sentinel, keys_a, sc());
             const int where = sort_pairs(nn, key_bits);
             keys_sorted = where ? keys_b : keys_a;
             int* ord = reinterpret_cast<int*>(where ? vals_b : vals_a);
@@ -342,7 +342,10 @@ struct bh_engine {
             BH_TRY(cudaMemsetAsync(arrived, 0, (size_t)M * sizeof(int), st));
             const BhTreeView t = view();
             k_emit<<<grid_for(n_in, 256), 256, 0, st>>>(t, root.levels);
-            k_climb<<<grid_for(n_in, 256), 256, 0, st>>>(t, root, x, y, m, jitter_active ? jflag : nullptr, leafpos);
+            if (climb_block)
+                k_climb_block<<<grid_for(n_in, CLIMB_B), CLIMB_B, 0, st>>>(t, root, x, y, m, jitter_active ? jflag : nullptr, leafpos);
+            else
+                k_climb<<<grid_for(n_in, 256), 256, 0, st>>>(t, root, x, y, m, jitter_active ? jflag : nullptr, leafpos);
             ctr.kernel_launches += 2;
         }
         BH_TRY(cudaEventRecord(ev[slot + 1], st));
@@ -351,6 +354,7 @@ struct bh_engine {
         return BH_OK;
     }
     int64_t ctr_rehomes = 0, ctr_reused = 0;
+    bool climb_block = true;        // BH_CLIMB_BLOCK=0: per-thread global climb (k_climb)
     int walk_group_min_waves = 0;   // BH_WALK_GROUP_MIN_WAVES > 0: group walk from this many waves of 128-thread blocks per SM
 
     int sort_pairs(int nn, int key_bits) {
@@ -568,6 +572,7 @@ int bh_create(const bh_config* cfg, bh_engine** out) {
     e->rehome_interval = e->cfg.rehome_interval > 0 ? e->cfg.rehome_interval : 8;
     if (const char* s = getenv("BH_REHOME_INTERVAL")) { const int v = atoi(s); if (v > 0) e->rehome_interval = v; }
     if (const char* s = getenv("BH_WALK_GROUP_MIN_WAVES")) e->walk_group_min_waves = atoi(s);
+    if (const char* s = getenv("BH_CLIMB_BLOCK")) e->climb_block = atoi(s) != 0;
     cudaError_t ce = cudaSetDevice(e->device);
     if (ce == cudaSuccess) ce = cudaStreamCreateWithFlags(&e->st, cudaStreamNonBlocking);
     for (auto& sl : e->ring) for (int k = 0; k < 16 && ce == cudaSuccess; ++k) ce = cudaEventCreate(&sl.e[k]);
@@ -828,7 +833,7 @@ int bh_get_morton(bh_engine* e, uint64_t* key, int32_t* depth, int32_t* order) {
     int rc = BH_OK;
     if (ce == cudaSuccess) {
         // sentinel here is the ABI's UINT64_MAX, not the sortable 1<<2L
-        k_keygen<<<grid_for(n, 256), 256, 0, e->st>>>(e->x, e->y, n, e->root, BH_KEY_NOT_IN_TREE, dkey, nullptr);
+        k_keygen<<<grid_for(n, 256), 256, 0, e->st>>>(e->x, e->y, n, e->root, bh_make_grid(e->root), BH_KEY_NOT_IN_TREE, dkey, nullptr);
         k_leaf_depth<<<grid_for(n, 256), 256, 0, e->st>>>(e->view(), e->leafpos, e->jitter_active ? e->jflag : nullptr, n, ddepth);
         k_scatter<uint64_t><<<grid_for(n, 256), 256, 0, e->st>>>(dkey_u, dkey, e->perm, n);
         ce = cudaGetLastError();

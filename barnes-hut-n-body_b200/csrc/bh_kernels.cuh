@@ -72,17 +72,28 @@ __device__ __forceinline__ int bh_tile_lookback(uint32_t* __restrict__ status, i
 // Morton keys by literal descent (BH.kt:153-155, :73-80) + root contains() (BH.kt:126).
 // HBM-bound: 16 B read + 8 B written per body.
 __global__ void __launch_bounds__(256) k_keygen(const double* __restrict__ x, const double* __restrict__ y, int n,
-                                                BhRoot root, uint64_t sentinel, uint64_t* __restrict__ keys,
+                                                BhRoot root, BhGrid grid, uint64_t sentinel, uint64_t* __restrict__ keys,
                                                 DevScalars* __restrict__ sc) {
-    const int b = blockIdx.x * blockDim.x + threadIdx.x;
-    bool in = false;
-    if (b < n) {
+    // grid-stride: ONE atomic per block for the in-box count (same-address atomics serialise in L2)
+    int cnt = 0;
+    for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < n; b += gridDim.x * blockDim.x) {
         const double px = x[b], py = y[b];
-        in = bh_root_contains(root, px, py);
-        keys[b] = in ? bh_morton_key(root, px, py) : sentinel;
+        const bool in = bh_root_contains(root, px, py);
+        // closed form on the exact grid when the root box allows it, else the literal descent
+        keys[b] = in ? (grid.exact ? bh_morton_key_grid(grid, root.levels, px, py) : bh_morton_key(root, px, py)) : sentinel;
+        cnt += in;
     }
-    const unsigned ball = __ballot_sync(0xffffffffu, in);
-    if (sc && (threadIdx.x & 31) == 0 && ball) atomicAdd(&sc->n_in, __popc(ball));
+    if (sc) {
+        __shared__ int s_cnt;
+        if (threadIdx.x == 0) s_cnt = 0;
+        __syncthreads();
+        int v = cnt;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if ((threadIdx.x & 31) == 0 && v) atomicAdd(&s_cnt, v);
+        __syncthreads();
+        if (threadIdx.x == 0 && s_cnt) atomicAdd(&sc->n_in, s_cnt);
+    }
 }
 
 // cnt(i) = max(0, delta(i) - delta(i-1)) and its exclusive scan S (single pass, decoupled
@@ -161,9 +172,18 @@ k_count_scan(const uint64_t* __restrict__ keys, int levels, DevScalars* __restri
         const int om = __shfl_xor_sync(0xffffffffu, maxd, o);
         maxd = om > maxd ? om : maxd;
     }
+    // one atomic per block (same-address atomics serialise in L2)
+    __shared__ int s_stat[2];
+    if (tid == 0) { s_stat[0] = 0; s_stat[1] = 0; }
+    __syncthreads();
     if (lane == 0) {
-        if (jit) atomicAdd(&sc->n_jitter, jit);
-        atomicMax(&sc->max_depth, maxd);
+        if (jit) atomicAdd(&s_stat[0], jit);
+        atomicMax(&s_stat[1], maxd);
+    }
+    __syncthreads();
+    if (tid == 0) {
+        if (s_stat[0]) atomicAdd(&sc->n_jitter, s_stat[0]);
+        atomicMax(&sc->max_depth, s_stat[1]);
     }
 }
 
@@ -186,6 +206,94 @@ __global__ void __launch_bounds__(256) k_climb(BhTreeView t, BhRoot root, const 
     // a body dropped by the jitter replay stays as a zero-mass ghost leaf (bh_jitter_cluster)
     const double mb = (jflag && (jflag[b] & 1)) ? 0.0 : m[b];
     bh_climb_body(t, root, i, x[b], y[b], mb);
+}
+
+// computeMass (BH.kt:173-202), block-local form.  A block owns CLIMB_B consecutive sorted bodies,
+// i.e. the contiguous preorder range [P0, P1) of the cells those bodies own.  A cell of that range
+// whose subtree ends inside it (skip <= P1) is LOCAL: ~97 % of the internal cells hold <= 32 bodies.
+// Local cells are computed entirely in shared memory with the same arrive-counter protocol as
+// bh_climb_from (the last arriving child sums the children 0..3 in order, the reference's f64
+// expression order) but with shared-memory atomics and block-scope fences instead of acq_rel
+// round trips to L2, and their records are written to HBM coalesced.  Only the roots of the local
+// subtrees continue through the global protocol (cells that span blocks).  A block whose range has
+// more than CLIMB_CAP cells falls back to bh_climb_body per thread.
+constexpr int CLIMB_B = 256;
+constexpr int CLIMB_CAP = 1024;
+__global__ void __launch_bounds__(CLIMB_B)
+k_climb_block(BhTreeView t, BhRoot root, const double* __restrict__ x, const double* __restrict__ y,
+              const double* __restrict__ m, const int* __restrict__ jflag, int* __restrict__ leafpos) {
+    __shared__ BhCellS s_sk[CLIMB_CAP];
+    __shared__ double s_m[CLIMB_CAP], s_x[CLIMB_CAP], s_y[CLIMB_CAP];
+    __shared__ int s_arr[CLIMB_CAP];
+    const int tid = threadIdx.x;
+    const int b0 = blockIdx.x * CLIMB_B;
+    const int b1 = min(b0 + CLIMB_B, t.n_in);
+    const int i = b0 + tid;
+    const int P0 = t.S[b0] + b0, P1 = t.S[b1] + b1;
+    const int nc = P1 - P0;
+    if (blockIdx.x == 0 && tid == 0) bh_write_terminal_cell(t);
+    int lp = 0;
+    double bx = 0.0, by = 0.0, bm = 0.0;
+    uint64_t key = 0;
+    if (i < b1) {
+        const int b = t.order[i];
+        lp = t.S[i + 1] + i;
+        leafpos[b] = lp;
+        bx = x[b]; by = y[b];
+        bm = (jflag && (jflag[b] & 1)) ? 0.0 : m[b];    // ghost leaf of a body the jitter replay dropped
+        key = t.keys[i];
+    }
+    if (nc > CLIMB_CAP) {                               // unusually deep range: per-thread global climb
+        if (i < b1) bh_climb_body(t, root, i, bx, by, bm);
+        return;
+    }
+    for (int c = tid; c < nc; c += CLIMB_B) { s_sk[c] = t.sk[P0 + c]; s_arr[c] = 0; }
+    __syncthreads();
+    // local climb; a thread that finishes the root of a local subtree keeps (rs, rcarry) for phase 3
+    BhCellS rs; rs.parent = -1; rs.skip = 0; rs.cnt = 0; rs.level = 0;
+    int rcarry = 0;
+    if (i < b1) {
+        int p = lp - P0;
+        BhCellS s = s_sk[p];
+        s_m[p] = bm; s_x[p] = bx; s_y[p] = by;
+        int carry = 1;
+        for (;;) {
+            const int q = s.parent;
+            if (q < 0) break;                                         // the root of the whole tree
+            if (q < P0 || s_sk[q - P0].skip > P1) { rs = s; rcarry = carry; break; }   // parent spans blocks
+            const BhCellS sq = s_sk[q - P0];
+            __threadfence_block();
+            const int old = atomicAdd(&s_arr[q - P0], carry);
+            if (old + carry != sq.cnt) break;
+            __threadfence_block();
+            double mSum = 0.0, sx = 0.0, sy = 0.0;
+            const int end = sq.skip - P0;
+            for (int ch = q - P0 + 1; ch < end; ch = s_sk[ch].skip - P0) {
+                const double mc = s_m[ch];
+                if (mc > 0.0) {   // BH.kt:189-192
+                    mSum = __dadd_rn(mSum, mc);
+                    sx = __dadd_rn(sx, __dmul_rn(s_x[ch], mc));
+                    sy = __dadd_rn(sy, __dmul_rn(s_y[ch], mc));
+                }
+            }
+            double cx, cy;
+            if (mSum > 0.0) { cx = __ddiv_rn(sx, mSum); cy = __ddiv_rn(sy, mSum); }     // BH.kt:194-196
+            else { double h; bh_cell_geometry(root, key, sq.level, &cx, &cy, &h); }    // BH.kt:197-200
+            s_m[q - P0] = mSum; s_x[q - P0] = cx; s_y[q - P0] = cy;
+            carry = sq.cnt;
+            s = sq;
+        }
+    }
+    __syncthreads();
+    // the finished local cells, coalesced
+    for (int c = tid; c < nc; c += CLIMB_B) {
+        const BhCellS s = s_sk[c];
+        if (s.skip <= P1) bh_write_cell(t, P0 + c, s_x[c], s_y[c], s_m[c], s.skip, s.level, s.skip == P0 + c + 1, root.half);
+    }
+    __threadfence();
+    __syncthreads();
+    // roots of the local subtrees report to their block-spanning parents (global protocol)
+    if (rcarry > 0) bh_climb_from(t, root, key, rs, rcarry);
 }
 
 // accumulateForce (BH.kt:215-239) + ax = fx/m (BH.kt:390-391): one thread per target body.

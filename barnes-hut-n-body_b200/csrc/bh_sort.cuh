@@ -21,7 +21,7 @@ constexpr int RADIX_BITS = 8;
 constexpr int RADIX = 1 << RADIX_BITS;
 constexpr int SORT_THREADS = 256;           // == RADIX: thread d owns digit d in the tile
 constexpr int SORT_WARPS = SORT_THREADS / 32;
-constexpr int SORT_IPT = 15;                // keys per thread
+constexpr int SORT_IPT = 12;                // keys per thread
 constexpr int SORT_TILE = SORT_THREADS * SORT_IPT;
 constexpr int MAX_PASSES = 8;
 
@@ -81,13 +81,20 @@ __global__ void __launch_bounds__(RADIX) k_histogram_scan(uint32_t* __restrict__
 // ---- one onesweep pass ----------------------------------------------------------------------
 // Sorts by the digit at `shift`.  vals_in == nullptr means "value = element index".
 // `ticket` and `lookback` (tiles*RADIX words) must be zero on entry.
+// Per tile: warp-striped load -> stable in-warp ranking by digit (match.any multi-split) ->
+// per-digit scan over the warps + decoupled look-back -> the tile is re-ordered by digit in
+// SHARED MEMORY -> the scatter to HBM writes runs of consecutive addresses (coalesced) instead of
+// one 8-byte store per key wherever its digit sends it.
 __global__ void __launch_bounds__(SORT_THREADS)
 k_onesweep_pass(const uint64_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
                 uint64_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out, int n, int shift,
                 const uint32_t* __restrict__ digit_base /* exclusive-scanned histogram of this pass */,
                 uint32_t* __restrict__ ticket, uint32_t* __restrict__ lookback) {
+    __shared__ uint64_t s_keys[SORT_TILE];          // re-used for the values (as uint32) afterwards
     __shared__ uint32_t s_hist[SORT_WARPS][RADIX];
-    __shared__ uint32_t s_base[RADIX];
+    __shared__ uint32_t s_base[RADIX];              // global position of the tile's first key of digit d
+    __shared__ uint32_t s_dstart[RADIX];            // position of digit d inside the re-ordered tile
+    __shared__ uint32_t s_wsum[SORT_WARPS];
     __shared__ uint32_t s_tile;
 
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
@@ -98,6 +105,7 @@ k_onesweep_pass(const uint64_t* __restrict__ keys_in, const uint32_t* __restrict
     const uint32_t tile = s_tile;
     const int64_t tile_base = (int64_t)tile * SORT_TILE;
     if (tile_base >= n) return;   // surplus block (whole block exits together)
+    const int tile_n = (int)((n - tile_base < SORT_TILE) ? (n - tile_base) : SORT_TILE);
 
     // warp-striped load: warp w owns SORT_IPT*32 consecutive elements
     uint64_t key[SORT_IPT];
@@ -112,7 +120,8 @@ k_onesweep_pass(const uint64_t* __restrict__ keys_in, const uint32_t* __restrict
         val[j] = ok ? (vals_in ? vals_in[idx] : (uint32_t)idx) : 0u;
     }
 
-    // stable in-warp ranking by digit (match.any multi-split), counts in the warp's histogram
+    // stable in-warp ranking by digit (match.any multi-split), counts in the warp's histogram.
+    // Padding keys (~0: digit 255) of the last tile rank behind every real key of their digit.
     const uint32_t lt_mask = (1u << lane) - 1u;
 #pragma unroll
     for (int j = 0; j < SORT_IPT; ++j) {
@@ -127,17 +136,21 @@ k_onesweep_pass(const uint64_t* __restrict__ keys_in, const uint32_t* __restrict
     __syncthreads();
 
     // thread d: exclusive scan of digit d over the warps, tile count, look-back
+    uint32_t dsum;
     {
         const int d = tid;
         uint32_t sum = 0;
 #pragma unroll
         for (int k = 0; k < SORT_WARPS; ++k) { const uint32_t c = s_hist[k][d]; s_hist[k][d] = sum; sum += c; }
+        dsum = sum;
+        // the padding keys of a partial tile were counted under digit 255: not part of the data
+        const uint32_t real = (d == RADIX - 1) ? sum - (uint32_t)(SORT_TILE - tile_n) : sum;
         uint32_t* mine = lookback + (size_t)tile * RADIX + d;
         uint32_t excl = 0;
         if (tile == 0) {
-            st_volatile_u32(mine, FLAG_PREFIX | sum);
+            st_volatile_u32(mine, FLAG_PREFIX | real);
         } else {
-            st_volatile_u32(mine, FLAG_AGG | sum);
+            st_volatile_u32(mine, FLAG_AGG | real);
             int64_t t = (int64_t)tile - 1;
             for (;;) {
                 const uint32_t v = ld_volatile_u32(lookback + (size_t)t * RADIX + d);
@@ -147,21 +160,58 @@ k_onesweep_pass(const uint64_t* __restrict__ keys_in, const uint32_t* __restrict
                 if (f == 2) break;                   // inclusive prefix: done
                 --t;
             }
-            st_volatile_u32(mine, FLAG_PREFIX | ((excl + sum) & VALUE_MASK));
+            st_volatile_u32(mine, FLAG_PREFIX | ((excl + real) & VALUE_MASK));
         }
         s_base[d] = digit_base[d] + excl;
     }
+    // exclusive scan of the tile's digit counts: where digit d starts in the re-ordered tile
+    {
+        uint32_t inc = dsum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += t;
+        }
+        if (lane == 31) s_wsum[w] = inc;
+        __syncthreads();
+        uint32_t wb = 0;
+#pragma unroll
+        for (int k = 0; k < SORT_WARPS; ++k) if (k < w) wb += s_wsum[k];
+        s_dstart[tid] = wb + inc - dsum;
+    }
     __syncthreads();
 
+    // re-order the tile by digit in shared memory
+    uint32_t lp[SORT_IPT];
 #pragma unroll
     for (int j = 0; j < SORT_IPT; ++j) {
-        const int64_t idx = warp_base + j * 32 + lane;
-        if (idx < n) {
-            const int d = (int)((key[j] >> shift) & (RADIX - 1));
-            const uint32_t dst = s_base[d] + s_hist[w][d] + rank[j];
-            keys_out[dst] = key[j];
-            vals_out[dst] = val[j];
+        const int d = (int)((key[j] >> shift) & (RADIX - 1));
+        lp[j] = s_dstart[d] + s_hist[w][d] + rank[j];
+        s_keys[lp[j]] = key[j];
+    }
+    __syncthreads();
+    // coalesced scatter: consecutive threads hold consecutive keys of the same digit
+    uint32_t dst[SORT_IPT];
+#pragma unroll
+    for (int j = 0; j < SORT_IPT; ++j) {
+        const int idx = tid + j * SORT_THREADS;
+        dst[j] = 0xffffffffu;
+        if (idx < tile_n) {
+            const uint64_t k = s_keys[idx];
+            const int d = (int)((k >> shift) & (RADIX - 1));
+            dst[j] = s_base[d] + ((uint32_t)idx - s_dstart[d]);
+            keys_out[dst[j]] = k;
         }
+    }
+    __syncthreads();
+    uint32_t* s_vals = reinterpret_cast<uint32_t*>(s_keys);
+#pragma unroll
+    for (int j = 0; j < SORT_IPT; ++j) s_vals[lp[j]] = val[j];
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < SORT_IPT; ++j) {
+        const int idx = tid + j * SORT_THREADS;
+        if (idx < tile_n) vals_out[dst[j]] = s_vals[idx];
     }
 }
 

@@ -125,6 +125,9 @@ def run_reference(args, rank, world):
 
 
 def main():
+    # NCCL prints a version banner on stdout when NCCL_DEBUG=VERSION; rank 0 must print ONE JSON line
+    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=None)

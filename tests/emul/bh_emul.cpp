@@ -23,6 +23,8 @@ struct Emul {
     std::vector<int> jflag;         // per body
     std::vector<int> jsorted;       // per sorted position (for the export)
     int n_ghost = 0, unsupported = 0;
+    int64_t grid_mismatch = 0;
+    int grid_exact = 0;
     BhTreeView view() {
         BhTreeView t{};
         t.keys = keys.data(); t.order = order.data(); t.S = S.data();
@@ -37,8 +39,14 @@ static void build(Emul& e, int n, const double* x, const double* y, const double
     e.root = BhRoot{rcx, rcy, rhalf, bh_key_levels(rhalf)};
     e.n = n;
     e.key_by_body.resize(n);
-    for (int b = 0; b < n; ++b)
+    const BhGrid grid = bh_make_grid(e.root);
+    for (int b = 0; b < n; ++b) {
         e.key_by_body[b] = bh_root_contains(e.root, x[b], y[b]) ? bh_morton_key(e.root, x[b], y[b]) : BH_KEY_NOT_IN_TREE;
+        // the closed-form key must agree with the literal descent whenever the grid is exact
+        if (grid.exact && e.key_by_body[b] != BH_KEY_NOT_IN_TREE &&
+            bh_morton_key_grid(grid, e.root.levels, x[b], y[b]) != e.key_by_body[b]) e.grid_mismatch++;
+    }
+    e.grid_exact = grid.exact;
     e.order.resize(n);
     std::iota(e.order.begin(), e.order.end(), 0);
     std::stable_sort(e.order.begin(), e.order.end(), [&](int a, int b) { return e.key_by_body[a] < e.key_by_body[b]; });
@@ -111,7 +119,8 @@ int bh_emul_accelerations(int n, const double* x, const double* y, const double*
     }
     for (int i = 0; i < e.n_in; ++i) if (depth_out && !(e.jflag[e.order[i]] & 1)) depth_out[e.order[i]] = e.sk[e.S[i + 1] + i].level;
     if (order_out) std::memcpy(order_out, e.order.data(), sizeof(int) * (size_t)n);
-    if (stats) { stats[0] = e.n_in - e.n_ghost; stats[1] = e.M; stats[2] = e.S[e.n_in]; stats[3] = tI; stats[4] = tO; stats[5] = tR; }
+    if (stats) { stats[0] = e.n_in - e.n_ghost; stats[1] = e.M; stats[2] = e.S[e.n_in]; stats[3] = tI; stats[4] = tO; stats[5] = tR;
+                 stats[6] = e.grid_exact; stats[7] = e.grid_mismatch; }
     return 0;
 }
 

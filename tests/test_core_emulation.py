@@ -25,7 +25,7 @@ def emul_acc(emul, scene, p, theta):
     n = len(x)
     out = dict(ax=np.empty(n), ay=np.empty(n), ci=np.empty(n, np.int32), co=np.empty(n, np.int32),
                key=np.empty(n, np.uint64), depth=np.empty(n, np.int32), order=np.empty(n, np.int32),
-               stats=np.zeros(6, np.int64))
+               stats=np.zeros(8, np.int64))
     emul.bh_emul_accelerations(n, _dp(x), _dp(y), _dp(m), C.c_double(p.root_cx), C.c_double(p.root_cy),
                                C.c_double(p.root_half), C.c_double(theta), C.c_double(p.soft2), C.c_double(p.G),
                                _dp(out["ax"]), _dp(out["ay"]), out["ci"].ctypes.data_as(I32), out["co"].ctypes.data_as(I32),
@@ -78,6 +78,7 @@ def test_core_matches_oracle(oracle_lib, emul_lib, name, gen, W, H, theta):
     g = emul_acc(emul_lib, scene, p, theta)
     # Morton order and cell assignment: bit-exact
     L = key_levels(p.root_half)
+    assert g["stats"][6] == 1 and g["stats"][7] == 0      # closed-form keys == literal descent
     assert (g["depth"] == depth).all()
     inb = depth >= 0
     assert ((g["key"][inb] >> (2 * (L - depth[inb])).astype(np.uint64)) == path[inb]).all()
@@ -163,3 +164,34 @@ def test_jitter_regime_matches_oracle(oracle_lib, emul_lib, name, scene, theta):
     assert k == len(to["cx"])
     for q in to:
         assert (tg[q] == to[q]).all(), q
+
+
+def test_closed_form_keys_on_cell_boundaries(oracle_lib, emul_lib):
+    """bh_morton_key_grid == the literal descent of BH.kt:153-155 for bodies ON cell boundaries of
+    every level and one ulp to either side (half = 1202 is not a power of two); a
+    root box whose grid is not exactly representable falls back to the descent."""
+    rng = np.random.default_rng(5)
+    half, cx, cy = 1202.0, 1200.0, 400.0
+    xs, ys = [], []
+    for level in range(1, 22):
+        w = 2 * half / 2 ** level
+        k = rng.integers(0, 2 ** level, 40)
+        bx = (cx - half) + k * w
+        by = (cy - half) + rng.integers(0, 2 ** level, 40) * w
+        for d in (-1, 0, 1):
+            xs.append(np.nextafter(bx, bx + d) if d else bx)
+            ys.append(np.nextafter(by, by + d) if d else by)
+    x = np.concatenate(xs); y = np.concatenate(ys)
+    scene = (x, y, np.zeros_like(x), np.zeros_like(x), np.ones_like(x))
+    o = make_engine(oracle_lib, scene, 2400, 800, flags=1, theta=0.5)
+    g = emul_acc(emul_lib, scene, o.params, 0.5)
+    assert g["stats"][6] == 1 and g["stats"][7] == 0
+    o.compute_accelerations()
+    depth, path = leaf_paths(oracle_lib, o)
+    inb = depth >= 0
+    L = key_levels(o.params.root_half)
+    assert ((g["key"][inb] >> (2 * (L - depth[inb])).astype(np.uint64)) == path[inb]).all()
+    # not exactly representable grid -> literal descent
+    o.set_params(root_cx=1200.1, root_half=1000.3)
+    g2 = emul_acc(emul_lib, scene, o.params, 0.5)
+    assert g2["stats"][6] == 0
