@@ -125,7 +125,8 @@ def bind(path: str) -> C.CDLL:
     return lib
 
 
-CUDA_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", "libbh_b200.so")
+# BH_B200_LIB: development override (A/B-testing a differently tuned build of the same library)
+CUDA_LIB_PATH = os.environ.get("BH_B200_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", "libbh_b200.so")
 _cuda_lib = None
 
 

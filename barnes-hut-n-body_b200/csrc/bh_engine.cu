@@ -48,7 +48,7 @@ inline int grid_for(int64_t n, int block) { return (int)((n + block - 1) / block
 
 constexpr int PAD = 64;            // slack behind every body array (in-place all-gather of padded slices)
 constexpr int MAX_WORLD = 64;
-enum HostFlag { HF_ZERO_MASS = 0, HF_N_DEAD = 1, HF_N_CAND = 2, HF_COUNT = 4 };
+enum HostFlag { HF_ZERO_MASS = 0, HF_N_DEAD = 1, HF_N_CAND = 2, HF_N_ROOTS = 3, HF_COUNT = 4 };
 
 }  // namespace
 
@@ -109,6 +109,8 @@ struct bh_engine {
     BhCellD* cd = nullptr;       // exact f64 records
     BhCellS* sk = nullptr;       // skeletons
     int* arrived = nullptr;
+    BhClimbRoot* climb_roots = nullptr;   // queue of finished local subtrees (k_climb_block -> k_climb_top)
+    int64_t climb_roots_cap = 0;
 
     bool tree_valid = false;
     BhRoot root{};
@@ -156,8 +158,8 @@ struct bh_engine {
         cap = 0;
     }
     void free_cells() {
-        dev_free(cell); dev_free(cd); dev_free(sk); dev_free(arrived);
-        cell_cap = 0;
+        dev_free(cell); dev_free(cd); dev_free(sk); dev_free(arrived); dev_free(climb_roots);
+        cell_cap = 0; climb_roots_cap = 0;
     }
 
 #define BH_TRY(expr)                                                        \
@@ -342,9 +344,19 @@ struct bh_engine {
             BH_TRY(cudaMemsetAsync(arrived, 0, (size_t)M * sizeof(int), st));
             const BhTreeView t = view();
             k_emit<<<grid_for(n_in, 256), 256, 0, st>>>(t, root.levels);
-            if (climb_block)
-                k_climb_block<<<grid_for(n_in, CLIMB_B), CLIMB_B, 0, st>>>(t, root, x, y, m, jitter_active ? jflag : nullptr, leafpos);
-            else
+            if (climb_block) {
+                if (n_in > climb_roots_cap) {
+                    dev_free(climb_roots);
+                    climb_roots_cap = std::max<int64_t>(n_in + n_in / 8, 1024);
+                    BH_TRY(dev_alloc(&climb_roots, (size_t)climb_roots_cap));
+                }
+                int* n_roots = dflags + HF_N_ROOTS;
+                BH_TRY(cudaMemsetAsync(n_roots, 0, sizeof(int), st));
+                k_climb_block<<<grid_for(n_in, CLIMB_B), CLIMB_B, 0, st>>>(t, root, x, y, m, jitter_active ? jflag : nullptr, leafpos,
+                                                                             climb_roots, n_roots);
+                k_climb_top<<<std::min(grid_for(n_in, 128 * 8), num_sms * 8), 128, 0, st>>>(t, root, climb_roots, n_roots);
+                ctr.kernel_launches += 1;
+            } else
                 k_climb<<<grid_for(n_in, 256), 256, 0, st>>>(t, root, x, y, m, jitter_active ? jflag : nullptr, leafpos);
             ctr.kernel_launches += 2;
         }
@@ -859,6 +871,19 @@ int bh_get_tree(bh_engine* e, int64_t cap, int64_t* n_cells, double* cx, double*
     if (!e) return BH_E_ARG;
     E_TRY(cudaSetDevice(e->device));
     if (!e->tree_valid) E_RC(bh_build_tree(e));   // lastTree ?: buildTree(), BH.kt:329-332
+    if (cap == 1 && e->M > 0) {   // root only (BHTree.mass / comX / comY, BH.kt:103-109): no full export
+        BhCellD r;
+        E_TRY(cudaMemcpy(&r, e->cd, sizeof(BhCellD), cudaMemcpyDeviceToHost));
+        if (cx) cx[0] = e->root.cx;
+        if (cy) cy[0] = e->root.cy;
+        if (h) h[0] = e->root.half;
+        if (mass) mass[0] = r.mass;
+        if (comx) comx[0] = r.comx;
+        if (comy) comy[0] = r.comy;
+        if (body) body[0] = e->M > 1 ? -2 : -3;   // -3: a single body-leaf (index not resolved here)
+        if (n_cells) *n_cells = 1;
+        return BH_OK;
+    }
     try {
         const size_t M = (size_t)e->M, ni = (size_t)e->n_in;
         std::vector<uint64_t> keys(ni);

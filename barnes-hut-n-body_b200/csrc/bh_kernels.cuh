@@ -219,9 +219,11 @@ __global__ void __launch_bounds__(256) k_climb(BhTreeView t, BhRoot root, const 
 // more than CLIMB_CAP cells falls back to bh_climb_body per thread.
 constexpr int CLIMB_B = 256;
 constexpr int CLIMB_CAP = 1024;
+struct alignas(16) BhClimbRoot { BhCellS s; uint64_t key; int carry, pad; };   // a finished local subtree
 __global__ void __launch_bounds__(CLIMB_B)
 k_climb_block(BhTreeView t, BhRoot root, const double* __restrict__ x, const double* __restrict__ y,
-              const double* __restrict__ m, const int* __restrict__ jflag, int* __restrict__ leafpos) {
+              const double* __restrict__ m, const int* __restrict__ jflag, int* __restrict__ leafpos,
+              BhClimbRoot* __restrict__ roots, int* __restrict__ n_roots) {
     __shared__ BhCellS s_sk[CLIMB_CAP];
     __shared__ double s_m[CLIMB_CAP], s_x[CLIMB_CAP], s_y[CLIMB_CAP];
     __shared__ int s_arr[CLIMB_CAP];
@@ -290,10 +292,33 @@ k_climb_block(BhTreeView t, BhRoot root, const double* __restrict__ x, const dou
         const BhCellS s = s_sk[c];
         if (s.skip <= P1) bh_write_cell(t, P0 + c, s_x[c], s_y[c], s_m[c], s.skip, s.level, s.skip == P0 + c + 1, root.half);
     }
-    __threadfence();
+    // The roots of the local subtrees still have to report to their block-spanning parents.  That
+    // is a chain of L2 round trips per level; doing it here would pin the block's shared memory
+    // for its whole length, so the roots are queued for k_climb_top instead (one slot reservation
+    // per block).
+    __shared__ int s_nroot, s_base_root;
+    if (tid == 0) s_nroot = 0;
     __syncthreads();
-    // roots of the local subtrees report to their block-spanning parents (global protocol)
-    if (rcarry > 0) bh_climb_from(t, root, key, rs, rcarry);
+    int slot = -1;
+    if (rcarry > 0) slot = atomicAdd(&s_nroot, 1);
+    __syncthreads();
+    if (tid == 0 && s_nroot) s_base_root = atomicAdd(n_roots, s_nroot);
+    __syncthreads();
+    if (slot >= 0) {
+        BhClimbRoot r; r.s = rs; r.key = key; r.carry = rcarry; r.pad = 0;
+        roots[s_base_root + slot] = r;
+    }
+}
+
+// The block-spanning top of the tree: every queued local root climbs with the global
+// arrive-counter protocol (bh_climb_from).  Runs after k_climb_block, so all local cells are visible.
+__global__ void __launch_bounds__(128)
+k_climb_top(BhTreeView t, BhRoot root, const BhClimbRoot* __restrict__ roots, const int* __restrict__ n_roots) {
+    const int n = *n_roots;
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+        const BhClimbRoot r = roots[k];
+        bh_climb_from(t, root, r.key, r.s, r.carry);
+    }
 }
 
 // accumulateForce (BH.kt:215-239) + ax = fx/m (BH.kt:390-391): one thread per target body.

@@ -24,6 +24,7 @@ constexpr int SORT_WARPS = SORT_THREADS / 32;
 constexpr int SORT_IPT = 12;                // keys per thread
 constexpr int SORT_TILE = SORT_THREADS * SORT_IPT;
 constexpr int MAX_PASSES = 8;
+constexpr int LOOKBACK_BATCH = 8;
 
 constexpr uint32_t FLAG_SHIFT = 30;
 constexpr uint32_t FLAG_AGG = 1u << FLAG_SHIFT;     // tile aggregate available
@@ -151,14 +152,27 @@ k_onesweep_pass(const uint64_t* __restrict__ keys_in, const uint32_t* __restrict
             st_volatile_u32(mine, FLAG_PREFIX | real);
         } else {
             st_volatile_u32(mine, FLAG_AGG | real);
+            // walk back over the predecessors, LOOKBACK_BATCH independent loads in flight at a time
+            // (when a whole wave of tiles starts together the walk is long: one L2 round trip per
+            // predecessor would serialise the pass)
             int64_t t = (int64_t)tile - 1;
-            for (;;) {
-                const uint32_t v = ld_volatile_u32(lookback + (size_t)t * RADIX + d);
-                const uint32_t f = v >> FLAG_SHIFT;
-                if (f == 0) continue;                // predecessor has not published yet
-                excl += v & VALUE_MASK;
-                if (f == 2) break;                   // inclusive prefix: done
-                --t;
+            bool done = false;
+            while (!done) {
+                uint32_t v[LOOKBACK_BATCH];
+#pragma unroll
+                for (int k = 0; k < LOOKBACK_BATCH; ++k)
+                    v[k] = (t - k >= 0) ? ld_volatile_u32(lookback + (size_t)(t - k) * RADIX + d) : FLAG_PREFIX;
+                int used = 0;
+#pragma unroll
+                for (int k = 0; k < LOOKBACK_BATCH; ++k) {
+                    if (done || used != k) continue;
+                    const uint32_t f = v[k] >> FLAG_SHIFT;
+                    if (f == 0) continue;            // not published yet: re-read from here
+                    excl += v[k] & VALUE_MASK;
+                    used = k + 1;
+                    if (f == 2) done = true;         // inclusive prefix: done
+                }
+                t -= used;
             }
             st_volatile_u32(mine, FLAG_PREFIX | ((excl + real) & VALUE_MASK));
         }

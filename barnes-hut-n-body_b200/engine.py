@@ -180,6 +180,17 @@ class NativeEngine:
         a["body"] = body
         return a
 
+    def tree_root(self) -> dict:
+        """mass / centre of mass of the root cell (BHTree.mass/comX/comY, BH.kt:103-109) without
+        exporting the whole tree."""
+        ncells = C.c_int64()
+        v = {k: np.empty(1, np.float64) for k in ("cx", "cy", "h", "mass", "comx", "comy")}
+        body = np.empty(1, np.int32)
+        rc = self.lib.bh_get_tree(self._h, 1, C.byref(ncells), _dp(v["cx"]), _dp(v["cy"]), _dp(v["h"]),
+                                  _dp(v["mass"]), _dp(v["comx"]), _dp(v["comy"]), _ip(body))
+        self._check(rc, "bh_get_tree")
+        return {k: float(a[0]) for k, a in v.items()}
+
     def counters(self) -> dict:
         c = BhCounters()
         self._check(self.lib.bh_get_counters(self._h, C.byref(c)), "bh_get_counters")
