@@ -83,6 +83,7 @@ SYMBOLS = {
     "bh_compute_accelerations": (C.c_int, [_H, _D, _D]),
     "bh_direct_sum": (C.c_int, [_H, _D, _D]),
     "bh_energy": (C.c_int, [_H, _D, _D, _D, _D]),
+    "bh_energy_tree": (C.c_int, [_H, C.c_double, _D, _D, _D, _D]),
     "bh_get_morton": (C.c_int, [_H, _U64, _I32, _I32]),
     "bh_get_tree": (C.c_int, [_H, C.c_int64, _I64, _D, _D, _D, _D, _D, _D, _I32]),
     "bh_build_tree": (C.c_int, [_H]),

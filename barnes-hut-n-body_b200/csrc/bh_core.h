@@ -656,6 +656,42 @@ BH_HD void bh_write_terminal_cell(const BhTreeView& t) {
     t.cell[t.M] = c;
 }
 
+// Potential of one body from the tree: the walk of bh_walk_body with m/sqrt(d^2+soft2) in place of
+// the force (same per-body decisions: guarded FP32 test, f64 re-test in the band).  Diagnostics
+// path (bh_energy_tree): plain code, FP32 terms folded into f64 every BH_WALK_CHUNK visits.
+BH_HD double bh_walk_potential(const BhTreeView& t, const BhWalkParams& w, double x, double y, int self, bool active) {
+    float xh, xl, yh, yl;
+    bh_split(x, &xh, &xl);
+    bh_split(y, &yh, &yl);
+    const float th2 = w.th2f, soft2 = w.soft2f;
+    const BhCell* __restrict__ cells = t.cell;
+    const int M = t.M;
+    int p = active ? 0 : M;
+    double phi = 0.0;
+    while (p < M) {
+        float f = 0.f;
+        for (int k = 0; k < BH_WALK_CHUNK && p < M; ++k) {
+            const BhCell c = cells[p];
+            const float dx = (c.xh - xh) + (c.xl - xl);
+            const float dy = (c.yh - yh) + (c.yl - yl);
+            const float d2 = fmaf(dx, dx, fmaf(dy, dy, soft2));
+            const float tt = fmaf(d2, th2, -c.s2);
+            bool accept = tt > 0.0f;
+            if (fabsf(tt) <= c.band) accept = bh_retest_cell(t.cd, t.sk, p, x, y, w.soft2, w.theta2, w.half);
+            if (accept && p != self && c.m != 0.0f) {
+                float inv = BH_RSQRTF(d2);
+#if defined(__CUDA_ARCH__)
+                inv = inv * fmaf(-0.5f * d2, inv * inv, 1.5f);   // one Newton step on MUFU.RSQ
+#endif
+                f = fmaf(c.m, inv, f);
+            }
+            p = accept ? c.skip : p + 1;
+        }
+        phi += (double)f;
+    }
+    return phi;
+}
+
 // ---- group walk: G bodies per thread, one shared preorder position ---------------------------
 // The per-lane walk above is bound by the L1 data stage: every lane of a warp is at a different
 // cell, so one warp-wide load touches ~15 distinct 32 B sectors.  Here a THREAD walks for G

@@ -831,6 +831,30 @@ int bh_energy(bh_engine* e, double* ke, double* pe, double* px, double* py) {
     return BH_OK;
 }
 
+int bh_energy_tree(bh_engine* e, double theta, double* ke, double* pe, double* px, double* py) {
+    if (!e) return BH_E_ARG;
+    E_TRY(cudaSetDevice(e->device));
+    double h[4] = {0, 0, 0, 0};
+    if (e->n > 0) {
+        E_RC(e->sync_velocities());
+        e->acc_valid = false;
+        E_RC(e->build());                               // buildTree() on the current state
+        E_RC(e->finish());
+        const BhWalkParams w = bh_walk_params(theta > 0.0 ? theta : e->par.theta, e->par.soft2, e->par.root_half);
+        E_TRY(cudaMemsetAsync(e->red, 0, 4 * sizeof(double), e->st));
+        k_energy_tree<<<grid_for(e->n, 128), 128, 0, e->st>>>(e->view(), w, (int)e->n, e->x, e->y, e->vx, e->vy, e->m, e->leafpos, e->red);
+        e->ctr.kernel_launches += 1;
+        E_TRY(cudaGetLastError());
+        E_TRY(cudaMemcpyAsync(h, e->red, sizeof(h), cudaMemcpyDeviceToHost, e->st));
+        E_TRY(cudaStreamSynchronize(e->st));
+    }
+    if (ke) *ke = h[0];
+    if (pe) *pe = -0.5 * e->par.G * h[1];
+    if (px) *px = h[2];
+    if (py) *py = h[3];
+    return BH_OK;
+}
+
 int bh_get_morton(bh_engine* e, uint64_t* key, int32_t* depth, int32_t* order) {
     if (!e) return BH_E_ARG;
     E_TRY(cudaSetDevice(e->device));

@@ -515,6 +515,34 @@ k_energy(const double* __restrict__ x, const double* __restrict__ y, const doubl
     }
 }
 
+// bh_energy_tree: phi_i from the tree, then out[0]=KE out[1]=sum m_i phi_i out[2]=px out[3]=py (f64)
+__global__ void __launch_bounds__(128)
+k_energy_tree(BhTreeView t, BhWalkParams w, int n, const double* __restrict__ x, const double* __restrict__ y,
+              const double* __restrict__ vx, const double* __restrict__ vy, const double* __restrict__ m,
+              const int* __restrict__ leafpos, double* __restrict__ out) {
+    __shared__ double red[4][4];
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    double v[4] = {0.0, 0.0, 0.0, 0.0};
+    if (b < n) {
+        const double phi = bh_walk_potential(t, w, x[b], y[b], leafpos[b], true);
+        const double mi = m[b];
+        v[0] = 0.5 * mi * (vx[b] * vx[b] + vy[b] * vy[b]);
+        v[1] = mi * phi;
+        v[2] = mi * vx[b];
+        v[3] = mi * vy[b];
+    }
+    const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        double s = v[q];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0) red[q][wp] = s;
+    }
+    __syncthreads();
+    if (threadIdx.x < 4) atomicAdd(&out[threadIdx.x], red[threadIdx.x][0] + red[threadIdx.x][1] + red[threadIdx.x][2] + red[threadIdx.x][3]);
+}
+
 // render read-back in USER order: xy[perm[i]] = (x, y), mf[perm[i]] = m
 __global__ void k_positions_f32(const double* __restrict__ x, const double* __restrict__ y, const double* __restrict__ m,
                                 const int* __restrict__ perm, int n, float2* __restrict__ xy, float* __restrict__ mf) {

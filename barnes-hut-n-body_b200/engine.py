@@ -155,6 +155,13 @@ class NativeEngine:
         ke, pe, px, py = (t.value for t in v)
         return {"kinetic": ke, "potential": pe, "total": ke + pe, "px": px, "py": py}
 
+    def energy_tree(self, theta: float = 0.0):
+        """Energy / momentum with the potential from the tree (O(N log N)); theta <= 0: the engine's."""
+        v = [C.c_double() for _ in range(4)]
+        self._check(self.lib.bh_energy_tree(self._h, float(theta), *[C.byref(t) for t in v]), "bh_energy_tree")
+        ke, pe, px, py = (t.value for t in v)
+        return {"kinetic": ke, "potential": pe, "total": ke + pe, "px": px, "py": py}
+
     # -- introspection ----------------------------------------------------------------
     def build_tree(self):
         self._check(self.lib.bh_build_tree(self._h), "bh_build_tree")

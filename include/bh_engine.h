@@ -161,6 +161,13 @@ int bh_compute_accelerations(bh_engine* e, double* ax, double* ay);
 int bh_direct_sum(bh_engine* e, double* ax, double* ay);
 /* E = sum 1/2 m v^2  -  1/2 G sum_{i!=j} m_i m_j / sqrt(r_ij^2 + soft2); momentum. */
 int bh_energy(bh_engine* e, double* kinetic, double* potential, double* px, double* py);
+/* The same diagnostics with the potential taken from the TREE (no reference counterpart; the
+ * all-pairs sum above is O(N^2)): phi_i is accumulated by the walk of BarnesHutAlg.kt:215-239 with
+ * 1/sqrt(d^2+soft2) in place of the force, on a tree built from the current state (buildTree(),
+ * :359-366 — including its jitter side effect), with opening angle `theta` (<= 0: the engine's).
+ * Sources are the bodies the tree holds (out-of-box bodies attract nobody, :126).  O(N log N):
+ * energy-drift tracking at 10M+ bodies. */
+int bh_energy_tree(bh_engine* e, double theta, double* kinetic, double* potential, double* px, double* py);
 
 /* ---- introspection (parity artefacts) ----------------------------------- */
 

@@ -599,6 +599,58 @@ int bh_energy(bh_engine* e, double* ke, double* pe, double* px, double* py) {
     return BH_OK;
 }
 
+// Potential analogue of accumulateForce (BH.kt:215-239): same pruning, self-skip and opening test,
+// m / sqrt(d^2 + soft2) in place of pointForceAcc.  (No reference counterpart: diagnostics.)
+static double treePotential(const BHTree* t, const Body* b, double theta2, double soft2) {
+    if (t->mass == 0.0) return 0.0;
+    const double dx = t->comX - b->x, dy = t->comY - b->y;
+    const double dist2 = dx * dx + dy * dy + soft2;
+    if (t->isLeaf()) {
+        if (t->body == nullptr || t->body == b) return 0.0;
+        return t->mass / std::sqrt(dist2);
+    }
+    const double side = t->quad.h * 2.0;
+    if (side * side < theta2 * dist2) return t->mass / std::sqrt(dist2);
+    double s = 0.0;
+    for (int c = 0; c < 4; ++c) s += treePotential(&t->children[c], b, theta2, soft2);
+    return s;
+}
+
+int bh_energy_tree(bh_engine* e, double theta, double* ke, double* pe, double* px, double* py) {
+    if (!e) return BH_E_ARG;
+    const double th = theta > 0.0 ? theta : e->par.theta;
+    double K = 0.0, U = 0.0, PX = 0.0, PY = 0.0;
+    try {
+        const BHTree* root = e->buildTree();
+        e->lastTree = const_cast<BHTree*>(root);
+        const int64_t n = (int64_t)e->bodies.size();
+        const int workers = (int)std::min<int64_t>(e->cores, std::max<int64_t>(n, 1));
+        std::vector<double> part((size_t)workers, 0.0);
+        std::atomic<int64_t> next{0};
+        auto work = [&](int w) {
+            double u = 0.0;
+            for (;;) {
+                const int64_t i0 = next.fetch_add(256, std::memory_order_relaxed);
+                if (i0 >= n) break;
+                const int64_t i1 = std::min(n, i0 + 256);
+                for (int64_t i = i0; i < i1; ++i) u += e->bodies[i].m * treePotential(root, &e->bodies[i], th * th, e->par.soft2);
+            }
+            part[(size_t)w] = u;
+        };
+        std::vector<std::thread> thr;
+        for (int w = 1; w < workers; ++w) thr.emplace_back(work, w);
+        work(0);
+        for (auto& t : thr) t.join();
+        for (double v : part) U += v;
+        for (const auto& b : e->bodies) { K += 0.5 * b.m * (b.vx * b.vx + b.vy * b.vy); PX += b.m * b.vx; PY += b.m * b.vy; }
+    } catch (const std::bad_alloc&) { return fail(e, BH_E_OOM, "bh_energy_tree: out of memory"); }
+    if (ke) *ke = K;
+    if (pe) *pe = -0.5 * e->par.G * U;
+    if (px) *px = PX;
+    if (py) *py = PY;
+    return BH_OK;
+}
+
 int bh_get_morton(bh_engine* e, uint64_t*, int32_t*, int32_t*) {
     // The oracle has no Morton keys: its observer is bh_ref_get_leaf_paths() below.
     return fail(e, BH_E_UNSUPPORTED, "bh_get_morton: the reference port has no Morton keys; use bh_ref_get_leaf_paths");

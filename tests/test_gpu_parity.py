@@ -433,3 +433,25 @@ def test_large_32m_cloud_properties(cuda_lib):
     assert d.max() < 1.0                      # dt = 0.005: nobody moved more than a pixel in one step
     px, py = (m * vx).sum(), (m * vy).sum()
     assert abs(px) + abs(py) < 1e-3 * (m * np.hypot(vx, vy)).sum()
+
+
+def test_tree_energy_matches_oracle_and_scales(oracle_lib, cuda_lib):
+    """bh_energy_tree: same decisions as the force walk, FP32 terms in f64 sums — potential within
+    1e-6 of the f64 oracle; O(N log N), so energy drift can be tracked at sizes where the pair sum
+    (bh_energy) is out of reach."""
+    scene = scenes.snap_f32(scenes.default_two_disks(n1=8000, n2=2000, seed=13))
+    o = make_engine(oracle_lib, scene, theta=0.5)
+    g = make_engine(cuda_lib, scene, theta=0.5)
+    for th in (0.5, 0.2, 1.0):
+        eo, eg = o.energy_tree(th), g.energy_tree(th)
+        assert abs(eg["potential"] - eo["potential"]) <= 1e-6 * abs(eo["potential"]), th
+        assert abs(eg["kinetic"] - eo["kinetic"]) <= 1e-12 * abs(eo["kinetic"])
+    d = g.energy()
+    assert abs(g.energy_tree(0.2)["potential"] - d["potential"]) <= 5e-4 * abs(d["potential"])
+    # 4M bodies: tree energy before / after 5 steps at dt = 0.001 (stable setting, H9)
+    big = scenes.make_uniform_random(4_000_000, 0.5, 4800, 1600, seed=15)
+    gb = make_engine(cuda_lib, big, 4800, 1600, theta=0.5, dt=0.001)
+    e0 = gb.energy_tree(0.3)
+    gb.step(5)
+    e1 = gb.energy_tree(0.3)
+    assert abs(e1["total"] - e0["total"]) <= 1e-4 * abs(e0["total"])

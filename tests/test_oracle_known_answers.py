@@ -185,3 +185,19 @@ def test_merge_rule(oracle_lib):
     e2 = make_engine(oracle_lib, _scene(b), theta=0.5, merge_min_dist=0.0, dt=0.0)
     e2.step(1)
     assert e2.n == 5
+
+
+def test_tree_potential_converges_to_the_pair_sum(oracle_lib):
+    """bh_energy_tree (walk of BH.kt:215-239 with 1/sqrt(d^2+soft2)): theta -> 0 reproduces the
+    all-pairs potential; at theta = 0.5 it is within the usual Barnes-Hut error; kinetic energy and
+    momentum are the same sums."""
+    from bh_b200 import scenes
+    scene = scenes.snap_f32(scenes.default_two_disks(n1=1500, n2=500, seed=9))
+    e = make_engine(oracle_lib, scene, theta=0.5)
+    d = e.energy()
+    t0 = e.energy_tree(1e-6)
+    t5 = e.energy_tree(0.5)
+    assert abs(t0["potential"] - d["potential"]) <= 1e-12 * abs(d["potential"])
+    assert abs(t5["potential"] - d["potential"]) <= 5e-3 * abs(d["potential"])      # monopole-only cells
+    assert t5["kinetic"] == d["kinetic"] and t5["px"] == d["px"] and t5["py"] == d["py"]
+    assert e.energy_tree()["potential"] == t5["potential"]          # theta <= 0: the engine's theta
