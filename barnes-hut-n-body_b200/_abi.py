@@ -79,6 +79,8 @@ SYMBOLS = {
     "bh_num_bodies": (C.c_int64, [_H]),
     "bh_get_origin": (C.c_int, [_H, C.c_int64, _I32, _I64]),
     "bh_get_positions_f32": (C.c_int, [_H, C.c_int64, _F, _F, _I64]),
+    "bh_request_positions_f32": (C.c_int, [_H]),
+    "bh_wait_positions_f32": (C.c_int, [_H, C.POINTER(C.POINTER(C.c_float)), C.POINTER(C.POINTER(C.c_float)), _I64]),
     "bh_step": (C.c_int, [_H, C.c_int32]),
     "bh_compute_accelerations": (C.c_int, [_H, _D, _D]),
     "bh_direct_sum": (C.c_int, [_H, _D, _D]),

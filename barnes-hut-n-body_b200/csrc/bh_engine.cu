@@ -135,6 +135,13 @@ struct bh_engine {
     bool acc_valid = false;          // ax/ay of this rank's slice = a(current positions, current params)
     bh_params acc_par{};             // parameters acc_valid refers to
 
+    // asynchronous render read-back (bh_request_positions_f32): dedicated staging + copy stream
+    cudaStream_t copy_st = nullptr;
+    cudaEvent_t snap_ev[2]{};        // [0] snapshot written (main stream), [1] copy finished (copy stream)
+    float2* snap_xy = nullptr; float* snap_m = nullptr;      // device staging
+    float* snap_hxy = nullptr; float* snap_hm = nullptr;     // pinned host
+    int64_t snap_cap = 0, snap_n = -1;
+
     bh_counters ctr{};
 
     int fail(int code, const char* what) { err = what; return code; }
@@ -616,6 +623,11 @@ void bh_destroy(bh_engine* e) {
     if (!e) return;
     cudaSetDevice(e->device);
     if (e->st) cudaStreamSynchronize(e->st);
+    if (e->copy_st) { cudaStreamSynchronize(e->copy_st); cudaStreamDestroy(e->copy_st); }
+    for (auto& ev : e->snap_ev) if (ev) cudaEventDestroy(ev);
+    dev_free(e->snap_xy); dev_free(e->snap_m);
+    if (e->snap_hxy) cudaFreeHost(e->snap_hxy);
+    if (e->snap_hm) cudaFreeHost(e->snap_hm);
     if (e->comm && bhcomm::api().ok) bhcomm::api().CommDestroy(e->comm);
     e->free_bodies();
     e->free_cells();
@@ -736,6 +748,53 @@ int bh_get_positions_f32(bh_engine* e, int64_t cap, float* xy, float* m, int64_t
     if (xy) E_TRY(cudaMemcpyAsync(xy, dxy, (size_t)e->n * sizeof(float2), cudaMemcpyDeviceToHost, e->st));
     if (m) E_TRY(cudaMemcpyAsync(m, dm, (size_t)e->n * sizeof(float), cudaMemcpyDeviceToHost, e->st));
     E_TRY(cudaStreamSynchronize(e->st));
+    return BH_OK;
+}
+
+int bh_request_positions_f32(bh_engine* e) {
+    if (!e) return BH_E_ARG;
+    E_TRY(cudaSetDevice(e->device));
+    if (!e->copy_st) {
+        E_TRY(cudaStreamCreateWithFlags(&e->copy_st, cudaStreamNonBlocking));
+        E_TRY(cudaEventCreateWithFlags(&e->snap_ev[0], cudaEventDisableTiming));
+        E_TRY(cudaEventCreateWithFlags(&e->snap_ev[1], cudaEventDisableTiming));
+    }
+    if (e->n > e->snap_cap) {
+        E_TRY(cudaStreamSynchronize(e->copy_st));
+        dev_free(e->snap_xy); dev_free(e->snap_m);
+        if (e->snap_hxy) cudaFreeHost(e->snap_hxy);
+        if (e->snap_hm) cudaFreeHost(e->snap_hm);
+        e->snap_hxy = e->snap_hm = nullptr;
+        const int64_t c = std::max<int64_t>(e->n + e->n / 8, 1024);
+        E_TRY(dev_alloc(&e->snap_xy, (size_t)c)); E_TRY(dev_alloc(&e->snap_m, (size_t)c));
+        E_TRY(cudaMallocHost((void**)&e->snap_hxy, (size_t)c * sizeof(float2)));
+        E_TRY(cudaMallocHost((void**)&e->snap_hm, (size_t)c * sizeof(float)));
+        e->snap_cap = c;
+    }
+    if (e->snap_n >= 0) E_TRY(cudaStreamWaitEvent(e->st, e->snap_ev[1], 0));   // previous copy still reads the staging
+    e->snap_n = e->n;
+    if (e->n > 0) {
+        k_positions_f32<<<grid_for(e->n, 256), 256, 0, e->st>>>(e->x, e->y, e->m, e->perm, (int)e->n, e->snap_xy, e->snap_m);
+        e->ctr.kernel_launches += 1;
+    }
+    E_TRY(cudaEventRecord(e->snap_ev[0], e->st));
+    E_TRY(cudaStreamWaitEvent(e->copy_st, e->snap_ev[0], 0));
+    if (e->n > 0) {
+        E_TRY(cudaMemcpyAsync(e->snap_hxy, e->snap_xy, (size_t)e->n * sizeof(float2), cudaMemcpyDeviceToHost, e->copy_st));
+        E_TRY(cudaMemcpyAsync(e->snap_hm, e->snap_m, (size_t)e->n * sizeof(float), cudaMemcpyDeviceToHost, e->copy_st));
+    }
+    E_TRY(cudaEventRecord(e->snap_ev[1], e->copy_st));
+    return BH_OK;
+}
+
+int bh_wait_positions_f32(bh_engine* e, const float** xy, const float** m, int64_t* n) {
+    if (!e) return BH_E_ARG;
+    if (e->snap_n < 0) return e->fail(BH_E_STATE, "bh_wait_positions_f32: no snapshot was requested");
+    E_TRY(cudaSetDevice(e->device));
+    E_TRY(cudaEventSynchronize(e->snap_ev[1]));
+    if (xy) *xy = e->snap_hxy;
+    if (m) *m = e->snap_hm;
+    if (n) *n = e->snap_n;
     return BH_OK;
 }
 

@@ -133,6 +133,21 @@ class NativeEngine:
                     "bh_get_positions_f32")
         return xy, m
 
+    def request_positions_f32(self):
+        """Start an asynchronous float snapshot of (x, y, m); overlaps the next step()."""
+        self._check(self.lib.bh_request_positions_f32(self._h), "bh_request_positions_f32")
+
+    def wait_positions_f32(self):
+        """(xy[n,2], m[n]) of the last requested snapshot (copies out of the engine's pinned buffers)."""
+        pxy, pm, n = C.POINTER(C.c_float)(), C.POINTER(C.c_float)(), C.c_int64()
+        self._check(self.lib.bh_wait_positions_f32(self._h, C.byref(pxy), C.byref(pm), C.byref(n)), "bh_wait_positions_f32")
+        k = n.value
+        if k == 0:
+            return np.empty((0, 2), np.float32), np.empty(0, np.float32)
+        xy = np.ctypeslib.as_array(pxy, shape=(k, 2)).copy()
+        m = np.ctypeslib.as_array(pm, shape=(k,)).copy()
+        return xy, m
+
     # -- compute ----------------------------------------------------------------------
     def step(self, nsteps: int = 1):
         self._check(self.lib.bh_step(self._h, nsteps), "bh_step")

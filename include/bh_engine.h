@@ -148,6 +148,14 @@ int bh_get_origin(bh_engine* e, int64_t cap, int32_t* origin, int64_t* n_out);
  * interleaved float (x,y) pairs and float masses. */
 int bh_get_positions_f32(bh_engine* e, int64_t cap, float* xy, float* m, int64_t* n_out);
 
+/* The same read-back, overlapped with the next step (the renderer of frame k runs while the
+ * engine computes frame k+1): bh_request_positions_f32 snapshots (x, y, m) as floats in list order
+ * and starts the device->host copy on a second stream; bh_step may be called right away;
+ * bh_wait_positions_f32 blocks until the snapshot is in host memory and returns pointers into
+ * engine-owned (pinned) buffers, valid until the next request. */
+int bh_request_positions_f32(bh_engine* e);
+int bh_wait_positions_f32(bh_engine* e, const float** xy, const float** m, int64_t* n);
+
 /* ---- compute ------------------------------------------------------------ */
 
 /* nsteps x PhysicsEngine.step() — BarnesHutAlg.kt:405-439: build+eval, half kick,

@@ -216,6 +216,8 @@ struct bh_engine {
     std::vector<int32_t> origin;   // observer: index at bh_set_bodies time of each surviving body
     bh_counters ctr{};
     std::string err;
+    std::vector<float> snapXY, snapM;   // bh_request_positions_f32 snapshot
+    int64_t snapN = -1;
     // host-staged multi-process protocol of include/bh_engine.h (no reference counterpart): this
     // rank evaluates and integrates only the list positions [lo, hi) of bh_slice_bounds
     int rank = 0, world = 1, phase = 0;
@@ -496,6 +498,26 @@ int bh_get_positions_f32(bh_engine* e, int64_t cap, float* xy, float* m, int64_t
         if (xy) { xy[2 * i] = (float)e->bodies[i].x; xy[2 * i + 1] = (float)e->bodies[i].y; }
         if (m) m[i] = (float)e->bodies[i].m;
     }
+    return BH_OK;
+}
+
+int bh_request_positions_f32(bh_engine* e) {
+    if (!e) return BH_E_ARG;
+    const size_t n = e->bodies.size();
+    e->snapXY.resize(2 * n); e->snapM.resize(n);
+    for (size_t i = 0; i < n; ++i) {
+        e->snapXY[2 * i] = (float)e->bodies[i].x; e->snapXY[2 * i + 1] = (float)e->bodies[i].y;
+        e->snapM[i] = (float)e->bodies[i].m;
+    }
+    e->snapN = (int64_t)n;
+    return BH_OK;
+}
+int bh_wait_positions_f32(bh_engine* e, const float** xy, const float** m, int64_t* n) {
+    if (!e) return BH_E_ARG;
+    if (e->snapN < 0) return fail(e, BH_E_STATE, "bh_wait_positions_f32: no snapshot was requested");
+    if (xy) *xy = e->snapXY.data();
+    if (m) *m = e->snapM.data();
+    if (n) *n = e->snapN;
     return BH_OK;
 }
 

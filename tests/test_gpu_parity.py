@@ -455,3 +455,22 @@ def test_tree_energy_matches_oracle_and_scales(oracle_lib, cuda_lib):
     gb.step(5)
     e1 = gb.energy_tree(0.3)
     assert abs(e1["total"] - e0["total"]) <= 1e-4 * abs(e0["total"])
+
+
+def test_async_render_readback_overlaps_the_next_step(oracle_lib, cuda_lib):
+    """bh_request_positions_f32 / bh_wait_positions_f32 (what NBodyPanel.paintComponent needs,
+    NBodyPanel.kt:302-306): the snapshot is the state at request time even though a step ran
+    before it was collected; list order survives re-homing and merges."""
+    scene = _merge_scene(seed=61, n1=4000, n2=1000)
+    for lib in (oracle_lib, cuda_lib):
+        e = make_engine(lib, scene, theta=0.5, merge_min_dist=8.0)
+        e.step(3)
+        x, y, vx, vy, m = e.get_bodies()
+        e.request_positions_f32()
+        e.step(2)                              # overlaps the copy
+        xy, mf = e.wait_positions_f32()
+        assert xy.shape == (len(x), 2)
+        assert (xy[:, 0] == x.astype(np.float32)).all() and (xy[:, 1] == y.astype(np.float32)).all()
+        assert (mf == m.astype(np.float32)).all()
+        xy2, _ = e.get_positions_f32()         # the synchronous read-back now shows the later state
+        assert (xy2[: min(len(xy2), len(xy))] != xy[: min(len(xy2), len(xy))]).any()
