@@ -42,6 +42,12 @@ class BhParams(C.Structure):
                                           "merge_max_mass", "merge_min_dist")]
 
 
+class BhDiskParams(C.Structure):
+    _fields_ = [(k, C.c_double) for k in ("x", "y", "vx", "vy", "r", "min_r", "central_mass", "total_satellite_mass",
+                                          "eps_m2", "phi0", "bar_taper_r", "radial_scale", "speed_jitter", "radial_jitter")] + \
+               [("clockwise", C.c_int32), ("kepler", C.c_int32)]
+
+
 class BhCounters(C.Structure):
     _fields_ = [("n_bodies", C.c_int64), ("n_in_tree", C.c_int64), ("n_out_of_box", C.c_int64),
                 ("n_jitter_bodies", C.c_int64), ("n_cells", C.c_int64), ("n_internal", C.c_int64),
@@ -79,6 +85,9 @@ SYMBOLS = {
     "bh_num_bodies": (C.c_int64, [_H]),
     "bh_get_origin": (C.c_int, [_H, C.c_int64, _I32, _I64]),
     "bh_get_positions_f32": (C.c_int, [_H, C.c_int64, _F, _F, _I64]),
+    "bh_default_disk_params": (C.c_int, [C.c_int32, C.c_int32, C.POINTER(BhDiskParams)]),
+    "bh_append_disk": (C.c_int, [_H, C.c_int64, C.POINTER(BhDiskParams), C.c_uint64]),
+    "bh_append_uniform_random": (C.c_int, [_H, C.c_int64, C.c_double, C.c_int32, C.c_int32, C.c_uint64]),
     "bh_request_positions_f32": (C.c_int, [_H]),
     "bh_wait_positions_f32": (C.c_int, [_H, C.POINTER(C.POINTER(C.c_float)), C.POINTER(C.POINTER(C.c_float)), _I64]),
     "bh_step": (C.c_int, [_H, C.c_int32]),

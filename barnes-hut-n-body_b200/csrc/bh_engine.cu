@@ -519,11 +519,14 @@ struct bh_engine {
     int excl_scan(const int* in, int nn, int* out);
     int merge_rule();
     int merge_done();
+    int grow_keep(int64_t extra);
+    int finish_append(int64_t added);
     int run_steps(int nsteps);
     void collect(EvSlot& sl);
 };
 
 #include "bh_merge.cuh"
+#include "bh_scene.cuh"
 
 // fold the timers of a finished step slot into the counters (waits for that step only)
 void bh_engine::collect(EvSlot& sl) {
@@ -749,6 +752,55 @@ int bh_get_positions_f32(bh_engine* e, int64_t cap, float* xy, float* m, int64_t
     if (m) E_TRY(cudaMemcpyAsync(m, dm, (size_t)e->n * sizeof(float), cudaMemcpyDeviceToHost, e->st));
     E_TRY(cudaStreamSynchronize(e->st));
     return BH_OK;
+}
+
+// ---- scene generators on the device (BodyFactory.kt) -------------------------------------------
+int bh_default_disk_params(int32_t w, int32_t h, bh_disk_params* p) {
+    if (!p) return BH_E_ARG;
+    memset(p, 0, sizeof(*p));
+    p->x = w * 0.5; p->y = h * 0.5;                      // BodyFactory.kt:75-76
+    p->r = 200.0; p->min_r = 8.0;                        // :77-78, Config.kt:35
+    p->central_mass = 50000.0; p->total_satellite_mass = 5000.0;   // Config.kt:32,38
+    p->eps_m2 = 0.03; p->phi0 = 0.0; p->bar_taper_r = 0.0; p->radial_scale = 0.0;   // :66-70
+    p->speed_jitter = 0.01; p->radial_jitter = 0.0; p->clockwise = 1; p->kepler = 0;   // :71-73
+    return BH_OK;
+}
+
+int bh_append_disk(bh_engine* e, int64_t n_total, const bh_disk_params* p, uint64_t seed) {
+    if (!e || !p) return e ? e->fail(BH_E_ARG, "bh_append_disk: bad arguments") : BH_E_ARG;
+    if (e->phase != 0) return e->fail(BH_E_STATE, "bh_append_disk: a step is in progress");
+    E_TRY(cudaSetDevice(e->device));
+    const int64_t add = std::max<int64_t>(n_total, 1);   // sats = (nTotal - 1).coerceAtLeast(0), plus the centre
+    if (e->n + add >= (int64_t)1 << 30) return e->fail(BH_E_ARG, "more than 2^30 bodies are not supported");
+    E_RC(e->sync_velocities());
+    E_RC(e->grow_keep(add));
+    const int64_t b = e->n;
+    const int na = (int)add;
+    // distances from the centre -> keys_a; sorted by radius with the engine's onesweep (64-bit keys)
+    k_gen_disk_positions<<<grid_for(na, 256), 256, 0, e->st>>>(na, *p, seed, e->x + b, e->y + b, e->vx + b, e->vy + b, e->m + b, e->keys_a);
+    if (na > 1) {
+        const int where = bhsort::onesweep_sort(e->keys_a, e->vals_a, e->keys_b, e->vals_b, na, 64, e->sort_scratch(), e->st, e->num_sms);
+        const uint32_t* by_radius = where ? e->vals_b : e->vals_a;
+        k_gen_disk_velocities<<<grid_for(na, 256), 256, 0, e->st>>>(na, *p, e->par.G, seed, by_radius, e->x + b, e->y + b, e->vx + b, e->vy + b);
+        e->ctr.kernel_launches += 12;
+    }
+    E_TRY(cudaGetLastError());
+    return e->finish_append(add);
+}
+
+int bh_append_uniform_random(bh_engine* e, int64_t n, double m, int32_t w, int32_t h, uint64_t seed) {
+    if (!e) return BH_E_ARG;
+    if (e->phase != 0) return e->fail(BH_E_STATE, "bh_append_uniform_random: a step is in progress");
+    if (n <= 0 || !(m > 0.0)) return BH_OK;              // BodyFactory.kt:165: empty list
+    E_TRY(cudaSetDevice(e->device));
+    if (e->n + n >= (int64_t)1 << 30) return e->fail(BH_E_ARG, "more than 2^30 bodies are not supported");
+    E_RC(e->sync_velocities());
+    E_RC(e->grow_keep(n));
+    const int64_t b = e->n;
+    k_gen_uniform<<<grid_for(n, 256), 256, 0, e->st>>>((int)n, (double)w, (double)h, m, seed, e->x + b, e->y + b, e->vx + b, e->vy + b, e->m + b);
+    e->ctr.kernel_launches += 1;
+    E_TRY(cudaGetLastError());
+    return e->finish_append(n);
 }
 
 int bh_request_positions_f32(bh_engine* e) {

@@ -21,7 +21,7 @@ from typing import Callable, List, Optional, Sequence
 import numpy as np
 
 from . import _abi
-from ._abi import BhConfig, BhCounters, BhError, BhParams
+from ._abi import BhConfig, BhCounters, BhDiskParams, BhError, BhParams
 
 
 def _dp(a: Optional[np.ndarray]):
@@ -132,6 +132,24 @@ class NativeEngine:
                                                   m.ctypes.data_as(C.POINTER(C.c_float)), C.byref(n_out)),
                     "bh_get_positions_f32")
         return xy, m
+
+    # -- scene generators on the device (BodyFactory.kt) -------------------------------------
+    def disk_params(self, width_px: int = 2400, height_px: int = 800, **kw) -> BhDiskParams:
+        p = BhDiskParams()
+        self._check(self.lib.bh_default_disk_params(width_px, height_px, C.byref(p)), "bh_default_disk_params")
+        for k, v in kw.items():
+            if not hasattr(p, k):
+                raise AttributeError(k)
+            setattr(p, k, type(getattr(p, k))(v))
+        return p
+
+    def append_disk(self, n_total: int, params: BhDiskParams, seed: int = 1):
+        """bodies += BodyFactory.makeGalaxyDisk / makeKeplerDisk(n_total, ...) generated on the device."""
+        self._check(self.lib.bh_append_disk(self._h, n_total, C.byref(params), seed), "bh_append_disk")
+
+    def append_uniform_random(self, n: int, m: float, width_px: int = 2400, height_px: int = 800, seed: int = 1):
+        """bodies += BodyFactory.makeUniformRandom(n, m) generated on the device."""
+        self._check(self.lib.bh_append_uniform_random(self._h, n, float(m), width_px, height_px, seed), "bh_append_uniform_random")
 
     def request_positions_f32(self):
         """Start an asynchronous float snapshot of (x, y, m); overlaps the next step()."""

@@ -156,6 +156,40 @@ int bh_get_positions_f32(bh_engine* e, int64_t cap, float* xy, float* m, int64_t
 int bh_request_positions_f32(bh_engine* e);
 int bh_wait_positions_f32(bh_engine* e, const float** xy, const float** m, int64_t* n);
 
+/* ---- scene generators on the device (BodyFactory.kt) ------------------------------
+ * The reference's UI injects bodies with resetBodies(old + BodyFactory.make...(...))
+ * (NBodyPanel.kt:228-234, :282-286).  These entry points do the same on the device, so 10M-100M
+ * body scenes never cross PCIe.  Kotlin's XorWow stream and the JDK's libm are not reproducible
+ * bit-for-bit (and the reference seeds them from the clock, BodyFactory.kt:74), so parity is
+ * DISTRIBUTIONAL: same sampling laws, a counter-based generator keyed by `seed`.
+ * New bodies are appended behind the existing ones in list order; afterwards bh_get_origin is
+ * the identity over the new list. */
+typedef struct bh_disk_params {
+    double x, y;                 /* centre                              (BodyFactory.kt:75-76)   */
+    double vx, vy;               /* drift velocity of the whole disk    (:75)                    */
+    double r;                    /* rMax                                (:77, default 200)       */
+    double min_r;                /* Config.MIN_R = 8                    (:78)                    */
+    double central_mass;         /* Config.CENTRAL_MASS = 50000         (:79)                    */
+    double total_satellite_mass; /* Config.TOTAL_SATELLITE_MASS = 5000  (:80)                    */
+    double eps_m2;               /* m=2 bar amplitude, 0.03             (:66)                    */
+    double phi0;                 /* bar phase                           (:67)                    */
+    double bar_taper_r;          /* <= 0: 0.6 r                         (:68, :93)               */
+    double radial_scale;         /* Rd; <= 0: r / 3                     (:70, :92)               */
+    double speed_jitter;         /* 0.01                                (:71)                    */
+    double radial_jitter;        /* 0                                   (:72)                    */
+    int32_t clockwise;           /* 1                                   (:73)                    */
+    int32_t kepler;              /* 1: makeKeplerDisk's law instead (uniform in area on
+                                  * [min_r, r], radius jittered by radial_jitter, :35-41)         */
+} bh_disk_params;
+/* defaults of makeGalaxyDisk (BodyFactory.kt:63-81) centred on a W x H window */
+int bh_default_disk_params(int32_t width_px, int32_t height_px, bh_disk_params* p);
+/* bodies += makeGalaxyDisk / makeKeplerDisk(n_total, ...): 1 central body + (n_total-1) satellites
+ * with circular speeds from the exact enclosed mass (:118-147); n_total <= 1: the central body only
+ * (the right-mouse-button "black hole", NBodyPanel.kt:171). */
+int bh_append_disk(bh_engine* e, int64_t n_total, const bh_disk_params* p, uint64_t seed);
+/* bodies += makeUniformRandom(n, m): x ~ U[0,W), y ~ U[0,H), v = 0 (BodyFactory.kt:160-177). */
+int bh_append_uniform_random(bh_engine* e, int64_t n, double m, int32_t width_px, int32_t height_px, uint64_t seed);
+
 /* ---- compute ------------------------------------------------------------ */
 
 /* nsteps x PhysicsEngine.step() — BarnesHutAlg.kt:405-439: build+eval, half kick,

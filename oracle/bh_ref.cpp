@@ -501,6 +501,19 @@ int bh_get_positions_f32(bh_engine* e, int64_t cap, float* xy, float* m, int64_t
     return BH_OK;
 }
 
+// The device scene generators have no oracle twin: their parity is distributional and is checked
+// against the numpy generators of scenes.py (tests/test_gpu_parity.py).
+int bh_default_disk_params(int32_t w, int32_t h, bh_disk_params* p) {
+    if (!p) return BH_E_ARG;
+    std::memset(p, 0, sizeof(*p));
+    p->x = w * 0.5; p->y = h * 0.5; p->r = 200.0; p->min_r = 8.0;
+    p->central_mass = 50000.0; p->total_satellite_mass = 5000.0;
+    p->eps_m2 = 0.03; p->speed_jitter = 0.01; p->clockwise = 1;
+    return BH_OK;
+}
+int bh_append_disk(bh_engine* e, int64_t, const bh_disk_params*, uint64_t) { return fail(e, BH_E_UNSUPPORTED, "bh_append_disk: device generator (use scenes.py with the reference port)"); }
+int bh_append_uniform_random(bh_engine* e, int64_t, double, int32_t, int32_t, uint64_t) { return fail(e, BH_E_UNSUPPORTED, "bh_append_uniform_random: device generator (use scenes.py with the reference port)"); }
+
 int bh_request_positions_f32(bh_engine* e) {
     if (!e) return BH_E_ARG;
     const size_t n = e->bodies.size();

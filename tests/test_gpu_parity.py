@@ -474,3 +474,53 @@ def test_async_render_readback_overlaps_the_next_step(oracle_lib, cuda_lib):
         assert (mf == m.astype(np.float32)).all()
         xy2, _ = e.get_positions_f32()         # the synchronous read-back now shows the later state
         assert (xy2[: min(len(xy2), len(xy))] != xy[: min(len(xy2), len(xy))]).any()
+
+
+def test_device_scene_generators_follow_bodyfactory(cuda_lib):
+    """bh_append_disk / bh_append_uniform_random (BodyFactory.kt:63-150, :160-177) on the device.
+    Kotlin's RNG stream is not reproducible, so: (i) the deterministic parts are checked exactly —
+    list order old + new, centre body, radius range, enclosed-mass circular speeds recomputed with
+    numpy from the generated positions; (ii) the sampling laws are compared with the numpy
+    generators of scenes.py (two-sample Kolmogorov-Smirnov on radius, angle, speed)."""
+    import bh_b200
+    from scipy import stats
+    e = bh_b200.NativeEngine(lib=cuda_lib)
+    e.set_params(theta=0.5, merge_min_dist=0.0)
+    old = scenes.make_uniform_random(1000, 0.5, seed=2)
+    e.set_bodies(*old)
+    n_total = 200_001
+    p = e.disk_params(2400, 800, r=300.0, x=1200.0, y=400.0)
+    e.append_disk(n_total, p, seed=7)
+    e.append_uniform_random(5000, 0.5, 2400, 800, seed=9)      # key C (NBodyPanel.kt:282-286)
+    e.append_disk(0, e.disk_params(2400, 800, x=100.0, y=700.0), seed=1)   # RMB black hole (:171)
+    x, y, vx, vy, m = e.get_bodies()
+    assert len(x) == 1000 + n_total + 5000 + 1
+    assert all((a[:1000] == b).all() for a, b in zip((x, y, vx, vy, m), old))          # old bodies first, untouched
+    d = slice(1000, 1000 + n_total)
+    dx, dy = x[d] - 1200.0, y[d] - 400.0
+    assert (x[d][0], y[d][0], m[d][0]) == (1200.0, 400.0, 50000.0) and vx[d][0] == 0.0
+    assert np.allclose(m[d][1:], 5000.0 / (n_total - 1), rtol=0, atol=0)
+    R = np.hypot(dx, dy)[1:]
+    assert R.min() >= 8.0 * 0.97 and R.max() <= 300.0 * 1.03
+    # exact enclosed mass -> circular speed within the +-1 % speed jitter, purely tangential, clockwise
+    order = np.argsort(np.hypot(dx, dy), kind="stable")
+    menc = np.empty(n_total); menc[order] = np.cumsum(m[d][order])
+    vc = np.sqrt(80.0 * menc[1:] / R)
+    v = np.hypot(vx[d][1:], vy[d][1:])
+    assert np.abs(v / vc - 1.0).max() <= 0.0100001
+    assert np.abs((vx[d][1:] * dx[1:] + vy[d][1:] * dy[1:]) / (v * R)).max() < 1e-12      # no radial velocity
+    assert ((dx[1:] * vy[d][1:] - dy[1:] * vx[d][1:]) < 0).all()                          # clockwise (BF.kt:138)
+    u = slice(1000 + n_total, 1000 + n_total + 5000)
+    assert (m[u] == 0.5).all() and (vx[u] == 0).all() and x[u].min() >= 0 and x[u].max() < 2400 and y[u].max() < 800
+    assert (x[-1], y[-1], m[-1]) == (100.0, 700.0, 50000.0)
+    # sampling laws vs the numpy generators
+    ref = scenes.make_galaxy_disk(n_total, x=1200.0, y=400.0, r=300.0, seed=11)
+    Rr = np.hypot(ref[0][1:] - 1200.0, ref[1][1:] - 400.0)
+    assert stats.ks_2samp(R, Rr).pvalue > 1e-3
+    assert stats.ks_2samp(np.arctan2(dy[1:], dx[1:]), np.arctan2(ref[1][1:] - 400.0, ref[0][1:] - 1200.0)).pvalue > 1e-3
+    assert stats.ks_2samp(v, np.hypot(ref[2][1:], ref[3][1:])).pvalue > 1e-3
+    assert stats.ks_2samp(x[u], scenes.make_uniform_random(5000, 0.5, seed=4)[0]).pvalue > 1e-3
+    # the generated scene is usable right away, and a Kepler disk can be appended too
+    e.append_disk(50_000, e.disk_params(2400, 800, kepler=1, radial_jitter=0.03, r=304.0), seed=3)
+    e.step(2)
+    assert e.n == len(x) + 50_000 and np.isfinite(e.get_bodies()[0]).all()
