@@ -279,3 +279,71 @@ extern "C" int bh_emul_group_stats(int n, const double* x, const double* y, cons
     out[0] = it / warps; out[1] = sec / it; out[2] = cost / warps; out[3] = gvis / warps; out[4] = lvis / warps;
     return 0;
 }
+
+// ---- design probe (not a test): distinct 128 B lines per warp iteration of the free-running per-lane
+// walk under alternative cell layouts.  layout 0 = preorder (the engine's), 1 = level order (BFS:
+// all cells of a level contiguous, siblings adjacent), 2 = level order within 3-level blocks
+// (van Emde Boas-like: subtrees of height 3 contiguous).  out = {iterations/warp, sectors/iter, lines/iter}
+extern "C" int bh_emul_layout_stats(int n, const double* x, const double* y, const double* m, double rcx, double rcy,
+                                    double rhalf, double theta, double soft2, int layout, int stride, double* out /*[3]*/) {
+    Emul e;
+    build(e, n, x, y, m, rcx, rcy, rhalf);
+    const double theta2 = theta * theta;
+    std::vector<int> pos(e.M);
+    std::iota(pos.begin(), pos.end(), 0);
+    if (layout == 1) {
+        std::vector<int> idx(e.M);
+        std::iota(idx.begin(), idx.end(), 0);
+        std::stable_sort(idx.begin(), idx.end(), [&](int a, int b) { return e.sk[a].level < e.sk[b].level; });
+        for (int k = 0; k < e.M; ++k) pos[idx[k]] = k;
+    } else if (layout == 2) {
+        // key = (level / 3, preorder position of the ancestor at level 3*(level/3), level, preorder)
+        std::vector<int> anc(e.M, 0);
+        std::vector<int> stack;   // ancestors by level
+        std::vector<int> top(64, 0);
+        for (int p = 0; p < e.M; ++p) {
+            const int L = e.sk[p].level;
+            top[L] = p;
+            anc[p] = top[(L / 3) * 3];
+        }
+        std::vector<int> idx(e.M);
+        std::iota(idx.begin(), idx.end(), 0);
+        std::stable_sort(idx.begin(), idx.end(), [&](int a, int b) {
+            const int ba = e.sk[a].level / 3, bb = e.sk[b].level / 3;
+            if (ba != bb) return ba < bb;
+            if (anc[a] != anc[b]) return anc[a] < anc[b];
+            return e.sk[a].level < e.sk[b].level;
+        });
+        for (int k = 0; k < e.M; ++k) pos[idx[k]] = k;
+    }
+    const int G = 32;
+    double it = 0, sec = 0, lin = 0;
+    int groups = 0;
+    for (int g0 = 0; g0 + G <= e.n_in; g0 += G * stride, ++groups) {
+        int p[G];
+        for (int l = 0; l < G; ++l) p[l] = 0;
+        for (;;) {
+            bool any = false;
+            int seen[G], ns = 0, lseen[G], nl = 0;
+            for (int l = 0; l < G; ++l) {
+                if (p[l] >= e.M) continue;
+                any = true;
+                const int q = p[l], a = pos[q];
+                bool dup = false;
+                for (int k = 0; k < ns; ++k) dup |= seen[k] == a;
+                if (!dup) seen[ns++] = a;
+                dup = false;
+                for (int k = 0; k < nl; ++k) dup |= lseen[k] == (a >> 2);
+                if (!dup) lseen[nl++] = a >> 2;
+                const int b = e.order[g0 + l];
+                const bool leafish = e.cell[q].s2 < 0;
+                const bool acc = leafish || bh_exact_accept(e.cd[q].comx, e.cd[q].comy, x[b], y[b], soft2, theta2, rhalf, e.sk[q].level);
+                p[l] = acc ? e.sk[q].skip : q + 1;
+            }
+            if (!any) break;
+            it += 1; sec += ns; lin += nl;
+        }
+    }
+    out[0] = it / groups; out[1] = sec / it; out[2] = lin / it;
+    return 0;
+}
