@@ -1,39 +1,9 @@
-# INTEGRATION — dropping the B200 engine into qwertukg/Barnes-Hut-N-Body
-
-The reference has no plugin/FFI layer: `NBodyPanel.kt` talks to the Kotlin classes of
-`BarnesHutAlg.kt` directly.  The drop-in keeps those class names and members and routes them to
-`libbh_b200.so` (C ABI in `include/bh_engine.h`).  A maintainer replaces **one file**
-(`BarnesHutAlg.kt`) with the façade below and adds one dependency (JNA); `NBodyPanel.kt`,
-`BodyFactory.kt`, `Config.kt`, `Main.kt` stay untouched.
-
-> No JVM/Kotlin toolchain exists in the build image, so the Kotlin below is compile-unverified
-> source.  The Python twin (`barnes-hut-n-body_b200/engine.py`) implements exactly the same
-> mapping and is what the tests exercise (`tests/test_gpu_parity.py::test_kotlin_facade_drives_the_engine`).
-
-## Mapping
-
-| reference member (file:line) | C ABI |
-|---|---|
-| `PhysicsEngine(initialBodies)` `BarnesHutAlg.kt:287` | `bh_create` + `bh_set_bodies` |
-| `step()` `:405-439` | `bh_set_params` (snapshot of `Config`, `:256,360-361,378,412`) + `bh_step(e, 1)` + `bh_get_bodies` + `bh_get_origin` |
-| `getBodies()` `:335` | the same `MutableList<Body>`, refreshed after `step()` |
-| `resetBodies(list)` `:342-349` | `bh_set_bodies` (any size, incl. 0) |
-| `getTreeForDebug()` `:329-332` + `visitQuads` `:265-274` | `bh_get_tree` (all cells incl. empty leaves, preorder) |
-| `mergeMaxMass`, `mergeMinDist` `:315,:321` | `bh_params.merge_max_mass / merge_min_dist` |
-| `BHTree.mass/comX/comY` `:103-109` | root row of `bh_get_tree` |
-
-## build.gradle.kts addition
-
-```kotlin
-dependencies { implementation("net.java.dev.jna:jna:5.14.0") }
-// run with -Djna.library.path=/path/to/barnes-hut-n-body_b200/csrc
-```
-
-## BarnesHutAlg.kt replacement (Kotlin + JNA direct mapping)
-
-The same source is shipped as `integration/kotlin/BarnesHutAlg.kt`.
-
-```kotlin
+// Drop-in replacement of /src/main/kotlin/BarnesHutAlg.kt of qwertukg/Barnes-Hut-N-Body: the same
+// classes and members (Body, Quad, BHTree, PhysicsEngine), routed to libbh_b200.so through JNA
+// direct mapping (C ABI: include/bh_engine.h).  NBodyPanel.kt, BodyFactory.kt, Config.kt and Main.kt
+// stay the reference's own files.  COMPILE-UNVERIFIED: no JVM/Kotlin toolchain exists in the image
+// this repository was built in; the Python twin barnes-hut-n-body_b200/engine.py implements the
+// same mapping and is what the tests exercise.  See INTEGRATION.md.
 import com.sun.jna.*
 import com.sun.jna.ptr.*
 
@@ -135,70 +105,3 @@ class PhysicsEngine(initialBodies: MutableList<Body>) {
         BHTree(cx, cy, h, ms, qx, qy).also { lastTree = it }
     }
 }
-```
-
-Cost of the façade per frame at the reference's scale (12.5 k bodies): 500 KB down per step.
-For large N a renderer should call `bh_get_positions_f32` (12 B/body) instead of `getBodies()`.
-
-## Python / ctypes binding (what the tests and bench use)
-
-`barnes-hut-n-body_b200/_abi.py` declares every symbol of the header (checked against the header
-by `tests/test_abi.py`), `engine.py` wraps a handle in `NativeEngine` (numpy SoA in/out) and
-mirrors the Kotlin API.  `import bh_b200` (root shim) loads the package, whose directory name
-`barnes-hut-n-body_b200` is not a valid Python identifier.
-
-```python
-import bh_b200
-from bh_b200 import Body, Config, PhysicsEngine
-Config.theta = 0.5
-eng = PhysicsEngine([Body(x, y, vx, vy, m) for ...])   # raises if libbh_b200.so / a GPU is missing
-eng.step(); eng.getTreeForDebug().visitQuads(draw)
-```
-
-## Multi-GPU / multi-process (one process per GPU)
-
-The tree is replicated, each rank walks and integrates a contiguous slice of the engine's
-Morton-ordered ("home") body order, one exchange of the drifted positions per step
-(DESIGN.md §6).  Results are bit-identical to a single process.
-
-```python
-import torch.distributed as dist, bh_b200
-from bh_b200.distributed import init_nccl_engine, HostStagedStepper
-
-# (a) NCCL inside the engine (CUDA library): torch.distributed only ships the 128-byte NCCL id
-eng = bh_b200.NativeEngine(device=local_rank)
-init_nccl_engine(eng, dist, rank, world)    # bh_comm_unique_id on rank 0 -> broadcast -> bh_comm_init
-eng.set_bodies(...)                         # every rank passes the same full state
-eng.step(k)                                 # replicated build, sliced walk, ncclAllGather per step
-
-# (b) host-staged transport (any library exporting the ABI, any torch.distributed backend)
-drv = HostStagedStepper(eng, dist, rank, world)   # bh_comm_init_external
-drv.step(k)     # bh_step_begin -> export/all_gather/import BH_FIELD_POS -> bh_step_end
-                #               -> export/all_gather/import BH_FIELD_VEL -> bh_step_finish
-```
-
-A JVM host would use (b) with its own transport, or (a) by passing the NCCL id through its own
-channel:
-
-```kotlin
-// rank 0: val id = ByteArray(128); BhNative.bh_comm_unique_id(id, 128); send id to the other ranks
-ck(BhNative.bh_comm_init(e, rank, world, id, 128))
-```
-
-## Pinning the oracle against the real reference (needs a JDK; not possible in the build image)
-
-The parity oracle (`oracle/bh_ref.cpp`) is a restatement of `BarnesHutAlg.kt` that could not be
-run against the JVM original here ("parity unpinned", DESIGN.md §2).  Anyone with a JDK can close
-that gap in three commands:
-
-```
-python tests/golden/jvm_roundtrip.py make /tmp/case.bin            # scene + parameters -> binary
-# in a checkout of the reference: copy integration/kotlin/HeadlessDump.kt to src/main/kotlin/, then
-./gradlew run -PmainClass=HeadlessDumpKt --args="/tmp/case.bin /tmp/case.out"   # or: kotlinc + java
-python tests/golden/jvm_roundtrip.py check /tmp/case.bin /tmp/case.out   # oracle vs JVM: bit-exact expected
-```
-
-`HeadlessDump.kt` uses the reference's own `PhysicsEngine`, `Config` and `Body` (no code of this
-repository), steps the scene and dumps the f64 state and the `visitQuads` cells; `check` replays
-the same input through the oracle and compares every double bit for bit (the path uses only
-IEEE `+ − × ÷ sqrt`, which a strict-FP JVM and `g++ -ffp-contract=off` evaluate identically).

@@ -7,7 +7,9 @@ import math
 import numpy as np
 import pytest
 
-from conftest import leaf_paths, make_engine
+import os
+
+from conftest import ROOT, leaf_paths, make_engine
 
 G = 80.0
 
@@ -201,3 +203,15 @@ def test_tree_potential_converges_to_the_pair_sum(oracle_lib):
     assert abs(t5["potential"] - d["potential"]) <= 5e-3 * abs(d["potential"])      # monopole-only cells
     assert t5["kinetic"] == d["kinetic"] and t5["px"] == d["px"] and t5["py"] == d["py"]
     assert e.energy_tree()["potential"] == t5["potential"]          # theta <= 0: the engine's theta
+
+
+def test_jvm_roundtrip_format(tmp_path, oracle_lib):
+    """tests/golden/jvm_roundtrip.py (the tool that pins the oracle against a real JVM run of the
+    reference): case / dump formats round-trip and `check` accepts the oracle's own dump."""
+    import subprocess
+    import sys
+    tool = os.path.join(ROOT, "tests", "golden", "jvm_roundtrip.py")
+    case, dump = str(tmp_path / "case.bin"), str(tmp_path / "case.out")
+    assert subprocess.call([sys.executable, tool, "make", case, "--steps", "2"]) == 0
+    assert subprocess.call([sys.executable, tool, "selftest", case, dump]) == 0
+    assert subprocess.call([sys.executable, tool, "check", case, dump]) == 0
