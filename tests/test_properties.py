@@ -31,7 +31,7 @@ def scenes_strategy(draw):
     return (x, y, np.zeros(n), np.zeros(n), np.array(masses, float)), theta
 
 
-@settings(max_examples=150, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture, HealthCheck.too_slow])
+@settings(max_examples=150, deadline=None, derandomize=True, database=None, suppress_health_check=[HealthCheck.function_scoped_fixture, HealthCheck.too_slow])
 @given(case=scenes_strategy())
 def test_core_equals_oracle_on_arbitrary_scenes(oracle_lib, emul_lib, case):
     scene, theta = case
