@@ -515,7 +515,7 @@ struct BhWalkResult { double ax, ay; int interactions, opened, retests; };
 #endif
 #define BH_WALK_CHUNK 16      // visits between two folds of the FP32 partial sums into f64
 
-#if defined(__CUDA_ARCH__)
+#if defined(__CUDACC__)
 // one 256-bit load of a whole 32-byte cell record (sm_100: LDG.E.256): one L1 wavefront per
 // distinct line instead of two
 __device__ __forceinline__ void bh_load_cell(const BhCell* __restrict__ c, float4* a, float4* b) {
@@ -655,6 +655,103 @@ BH_HD void bh_write_terminal_cell(const BhTreeView& t) {
     c.xh = 0.f; c.yh = 0.f; c.m = 0.f; c.s2 = -1.0f; c.xl = 0.f; c.yl = 0.f; c.skip = t.M; c.band = 0.0f;
     t.cell[t.M] = c;
 }
+
+// ---- lane-group walk: LG adjacent lanes (= LG Morton-adjacent bodies) share ONE position ---------
+// The per-lane walk is bound by the L1 data stage: the 32 lanes of a warp are at ~15 different
+// cells per iteration and every distinct sector costs a data-stage cycle.  Here the LG lanes of a
+// group walk in lockstep: a cell is opened when ANY un-muted lane of the group opens it; a lane
+// that accepts a cell its group opens takes the interaction and is muted (`mute` = skip of that
+// cell) until the walk leaves the subtree.  Per-body decisions — the set and order of each body's
+// interactions — are exactly those of the per-lane walk; a warp now touches at most 32/LG
+// sectors per iteration at the price of the union of the group's cells (probe
+// bh_emul_group_stats: 1.24x the iterations for LG = 4) and ~7 instructions of group logic.
+// second half of a visit: operands  %0 fx  %1 fy  %2 interactions  %3 opened  %4 p  %5 mute  |
+// %6 t  %7 self  %8 d2  %9 m  %10 dx  %11 dy  %12 skip  %13 shift of the group's bits in a ballot
+#define BH_LANEGROUP_VISIT_ASM()                                                                \
+    asm volatile(                                                                               \
+        "{\n\t"                                                                                 \
+        ".reg .pred Pu, P0, Pw, Pg, P1;\n\t"                                                    \
+        ".reg .f32 te, inv, t1, t2, wg;\n\t"                                                    \
+        ".reg .b32 bal;\n\t"                                                                    \
+        ".reg .s32 p1;\n\t"                                                                     \
+        "setp.ge.s32 Pu, %4, %5;\n\t"                  /* un-muted                         */   \
+        "selp.f32 te, %6, 0f7FC00000, Pu;\n\t"         /* muted: neither accepts nor opens */   \
+        "setp.gt.f32 P0, te, 0f00000000;\n\t"          /* accepts                          */   \
+        "setp.lt.f32 Pw, te, 0f00000000;\n\t"          /* wants the cell opened            */   \
+        "vote.sync.ballot.b32 bal, Pw, 0xffffffff;\n\t"                                         \
+        "shr.b32 bal, bal, %13;\n\t"                                                            \
+        "and.b32 bal, bal, %14;\n\t"                                                            \
+        "setp.ne.u32 Pg, bal, 0;\n\t"                  /* some lane of MY group opens it   */   \
+        "setp.ne.and.s32 P1, %4, %7, P0;\n\t"          /* ... not the body's own leaf      */   \
+        "setp.neu.and.f32 P1, %9, 0f00000000, P1;\n\t" /* ... and mass != 0 (BH.kt:216)    */   \
+        "rsqrt.approx.ftz.f32 inv, %8;\n\t"                                                     \
+        BH_LANEGROUP_NEWTON_ASM                                                                 \
+        "mul.f32 wg, %9, inv;\n\t"                                                              \
+        "mul.f32 wg, wg, inv;\n\t"                                                              \
+        "mul.f32 wg, wg, inv;\n\t"                                                              \
+        "@P1 fma.rn.f32 %0, wg, %10, %0;\n\t"                                                   \
+        "@P1 fma.rn.f32 %1, wg, %11, %1;\n\t"                                                   \
+        "@P1 add.s32 %2, %2, 1;\n\t"                                                            \
+        "@Pw add.s32 %3, %3, 1;\n\t"                                                            \
+        "@P0 mov.s32 %5, %12;\n\t"                     /* muted until the walk leaves the cell */ \
+        "add.s32 p1, %4, 1;\n\t"                                                                \
+        "selp.s32 %4, p1, %12, Pg;\n\t"                                                         \
+        "}"                                                                                     \
+        : "+f"(fx), "+f"(fy), "+r"(ni), "+r"(no), "+r"(p), "+r"(mute)                           \
+        : "f"(tt), "r"(self), "f"(d2), "f"(a.z), "f"(dx), "f"(dy), "r"(__float_as_int(b.z)),    \
+          "r"(gshift), "r"(gmask))
+#if BH_WALK_NEWTON
+#define BH_LANEGROUP_NEWTON_ASM                                                                 \
+    "mul.f32 t2, inv, inv;\n\t"                                                                 \
+    "fma.rn.f32 t1, %8, t2, 0fC0400000;\n\t"                                                    \
+    "mul.f32 inv, inv, t1;\n\t"
+#else
+#define BH_LANEGROUP_NEWTON_ASM ""
+#endif
+
+#if defined(__CUDACC__)
+// `group_active`: some lane of this lane's group has a target; `active`: this lane has one.
+template <int LG>
+__device__ __forceinline__ BhWalkResult bh_walk_lanegroup(const BhTreeView& t, const BhWalkParams& w, double x, double y,
+                                                          int self, bool active, bool group_active, int zero) {
+    float xh, xl, yh, yl;
+    bh_split(x, &xh, &xl);
+    bh_split(y, &yh, &yl);
+    BH_OPAQUE_F(xh); BH_OPAQUE_F(xl); BH_OPAQUE_F(yh); BH_OPAQUE_F(yl);
+    BhWalkResult r; r.ax = 0.0; r.ay = 0.0; r.interactions = 0; r.opened = 0; r.retests = 0;
+    const float th2 = w.th2f, soft2 = w.soft2f;
+    const BhCell* __restrict__ cells = t.cell + zero;      // `zero`: see bh_walk_body
+    const int M = t.M;
+    const int gshift = (threadIdx.x & 31) & ~(LG - 1);
+    const int gmask = (1 << LG) - 1;
+    int p = group_active ? 0 : M;
+    int mute = active ? 0 : 0x7fffffff;                     // surplus lanes stay muted for ever
+    int ni = 0, no = 0;
+    while (__any_sync(0xffffffffu, p < M)) {
+        float fx = 0.f, fy = 0.f;
+#pragma unroll
+        for (int k = 0; k < BH_WALK_CHUNK; ++k) {
+            float4 a, b;
+            bh_load_cell(cells + p, &a, &b);
+            const float dx = (a.x - xh) + (b.x - xl);
+            const float dy = (a.y - yh) + (b.y - yl);
+            const float d2 = fmaf(dx, dx, fmaf(dy, dy, soft2));
+            float tt = fmaf(d2, th2, -a.w);
+            if (fabsf(tt) <= b.w) {   // borderline: the reference's f64 test decides
+                tt = bh_retest_cell(t.cd, t.sk, p, x, y, w.soft2, w.theta2, w.half) ? 1.0f : -1.0f;
+                r.retests += (p >= mute);
+            }
+            BH_LANEGROUP_VISIT_ASM();
+        }
+        r.ax += (double)fx; r.ay += (double)fy;
+    }
+    r.interactions = ni; r.opened = no;
+#if BH_WALK_NEWTON
+    r.ax *= -0.125; r.ay *= -0.125;
+#endif
+    return r;
+}
+#endif
 
 // Potential of one body from the tree: the walk of bh_walk_body with m/sqrt(d^2+soft2) in place of
 // the force (same per-body decisions: guarded FP32 test, f64 re-test in the band).  Diagnostics

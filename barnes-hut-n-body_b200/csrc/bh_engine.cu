@@ -374,6 +374,7 @@ struct bh_engine {
     }
     int64_t ctr_rehomes = 0, ctr_reused = 0;
     bool climb_block = true;        // BH_CLIMB_BLOCK=0: per-thread global climb (k_climb)
+    bool walk_lanegroup = false;     // BH_WALK_LANEGROUP=1: 4 adjacent lanes share one position (bh_walk_lanegroup)
     int walk_group_min_waves = 0;   // BH_WALK_GROUP_MIN_WAVES > 0: group walk from this many waves of 128-thread blocks per SM
 
     int sort_pairs(int nn, int key_bits) {
@@ -414,6 +415,9 @@ struct bh_engine {
                     k_walk_group<true><<<g, 128, 0, st>>>(view(), w, (int)first, (int)count, x, y, m, leafpos, par.G, ax, ay, cntI, cntO, sc(), tot);
                 else
                     k_walk_group<false><<<g, 128, 0, st>>>(view(), w, (int)first, (int)count, x, y, m, leafpos, par.G, ax, ay, cntI, cntO, sc(), tot);
+            } else if (walk_lanegroup) {
+                const int g = grid_for(count, 128);
+                k_walk_lanegroup<<<g, 128, 0, st>>>(view(), w, (int)first, (int)count, x, y, m, leafpos, par.G, ax, ay, cntI, cntO, sc(), tot);
             } else {
                 const int g = grid_for(count, 128);
                 k_walk<<<g, 128, 0, st>>>(view(), w, (int)first, (int)count, x, y, m, leafpos, par.G, ax, ay, cntI, cntO, sc(), tot);
@@ -595,6 +599,7 @@ int bh_create(const bh_config* cfg, bh_engine** out) {
     if (const char* s = getenv("BH_REHOME_INTERVAL")) { const int v = atoi(s); if (v > 0) e->rehome_interval = v; }
     if (const char* s = getenv("BH_WALK_GROUP_MIN_WAVES")) e->walk_group_min_waves = atoi(s);
     if (const char* s = getenv("BH_CLIMB_BLOCK")) e->climb_block = atoi(s) != 0;
+    if (const char* s = getenv("BH_WALK_LANEGROUP")) e->walk_lanegroup = atoi(s) != 0;
     cudaError_t ce = cudaSetDevice(e->device);
     if (ce == cudaSuccess) ce = cudaStreamCreateWithFlags(&e->st, cudaStreamNonBlocking);
     for (auto& sl : e->ring) for (int k = 0; k < 16 && ce == cudaSuccess; ++k) ce = cudaEventCreate(&sl.e[k]);

@@ -359,6 +359,41 @@ k_walk(BhTreeView t, BhWalkParams w, int first_target, int n_targets, const doub
     }
 }
 
+// The same evaluation with groups of WALK_LG adjacent lanes sharing one position (bh_walk_lanegroup).
+constexpr int WALK_LG = 4;
+__global__ void __launch_bounds__(128)
+k_walk_lanegroup(BhTreeView t, BhWalkParams w, int first_target, int n_targets, const double* __restrict__ x,
+                 const double* __restrict__ y, const double* __restrict__ m, const int* __restrict__ leafpos, double G,
+                 double* __restrict__ ax, double* __restrict__ ay, int* __restrict__ cntI, int* __restrict__ cntO,
+                 DevScalars* __restrict__ sc, DevTotals* __restrict__ tot) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    int ni = 0, no = 0, nr = 0;
+    const bool active = k < n_targets;
+    const bool group_active = (k & ~(WALK_LG - 1)) < n_targets;
+    const int b = first_target + (active ? k : 0);
+    const BhWalkResult r = bh_walk_lanegroup<WALK_LG>(t, w, x[b], y[b], leafpos[b], active, group_active, (int)sc->pad);
+    if (active) {
+        const double mb = m[b];
+        ax[b] = (mb == 0.0) ? nan("") : G * r.ax;      // BH.kt:390-391: 0/0 = NaN for m == 0
+        ay[b] = (mb == 0.0) ? nan("") : G * r.ay;
+        ni = r.interactions; no = r.opened; nr = r.retests;
+        if (cntI) { cntI[b] = ni; cntO[b] = no; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        ni += __shfl_xor_sync(0xffffffffu, ni, o);
+        no += __shfl_xor_sync(0xffffffffu, no, o);
+        nr += __shfl_xor_sync(0xffffffffu, nr, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(&sc->interactions, (unsigned long long)ni);
+        atomicAdd(&sc->opened, (unsigned long long)no);
+        atomicAdd(&tot->interactions, (unsigned long long)ni);
+        atomicAdd(&tot->opened, (unsigned long long)no);
+        if (nr) { atomicAdd(&sc->retests, (unsigned long long)nr); atomicAdd(&tot->retests, (unsigned long long)nr); }
+    }
+}
+
 // The same evaluation with WALK_G bodies per thread (bh_walk_group): used when there are enough
 // targets to fill the machine with a quarter of the threads.
 constexpr int WALK_G = 4;
