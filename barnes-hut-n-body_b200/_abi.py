@@ -91,6 +91,7 @@ SYMBOLS = {
     "bh_request_positions_f32": (C.c_int, [_H]),
     "bh_wait_positions_f32": (C.c_int, [_H, C.POINTER(C.POINTER(C.c_float)), C.POINTER(C.POINTER(C.c_float)), _I64]),
     "bh_step": (C.c_int, [_H, C.c_int32]),
+    "bh_step_io": (C.c_int, [_H, C.c_int32, C.c_int64, _D, _D, _D, _D, _D, C.c_int64, _D, _D, _D, _D, _D, _I64]),
     "bh_compute_accelerations": (C.c_int, [_H, _D, _D]),
     "bh_direct_sum": (C.c_int, [_H, _D, _D]),
     "bh_energy": (C.c_int, [_H, _D, _D, _D, _D]),
@@ -126,7 +127,10 @@ class CudaLibraryMissing(ImportError):
 
 def bind(path: str) -> C.CDLL:
     """dlopen `path` and attach the signatures of every ABI symbol (raises if one is missing)."""
-    lib = C.CDLL(path, mode=C.RTLD_GLOBAL if hasattr(C, "RTLD_GLOBAL") else 0)
+    # RTLD_LOCAL: the product library and the oracle export the SAME symbol names (one ABI); global
+    # binding would let one library's internal calls land in the other (both are also linked with
+    # -Bsymbolic-functions for that reason)
+    lib = C.CDLL(path, mode=getattr(os, "RTLD_LOCAL", 0) | getattr(os, "RTLD_NOW", 2))
     for name, (res, args) in SYMBOLS.items():
         fn = getattr(lib, name)  # AttributeError if the symbol is not exported
         fn.restype = res

@@ -135,6 +135,22 @@ struct bh_engine {
     bool acc_valid = false;          // ax/ay of this rank's slice = a(current positions, current params)
     bh_params acc_par{};             // parameters acc_valid refers to
 
+    // bh_step_io: transfers overlapped with the compute
+    double* io_stage[4] = {nullptr, nullptr, nullptr, nullptr};   // staging for (vx, vy, m) in / (x, y, m, vy) out
+    int64_t io_cap = 0;
+    cudaEvent_t io_ev[2]{};          // [0] (vx, vy, m) arrived, [1] final positions written
+    bool io_wait_in = false;         // the compute stream has not yet waited for (vx, vy, m)
+    struct IoOut { double *x = nullptr, *y = nullptr, *m = nullptr; bool armed = false; } io_out;
+    int wait_inputs() {              // before the first kernel that reads vx / vy / m
+        if (io_wait_in) {
+            const cudaError_t ce = cudaStreamWaitEvent(st, io_ev[0], 0);
+            if (ce != cudaSuccess) return cuda_fail(ce, "cudaStreamWaitEvent");
+            io_wait_in = false;
+        }
+        return BH_OK;
+    }
+    int emit_positions_out();        // after the last drift: (x, y, m) -> host on the copy stream
+
     // asynchronous render read-back (bh_request_positions_f32): dedicated staging + copy stream
     cudaStream_t copy_st = nullptr;
     cudaEvent_t snap_ev[2]{};        // [0] snapshot written (main stream), [1] copy finished (copy stream)
@@ -297,7 +313,7 @@ struct bh_engine {
         tree_valid = false;
         root = BhRoot{par.root_cx, par.root_cy, par.root_half, bh_key_levels(par.root_half)};
         const int nn = (int)n;
-        if (rehome_due && nn > 0) BH_RC(sync_velocities());
+        if (rehome_due && nn > 0) { BH_RC(sync_velocities()); BH_RC(wait_inputs()); }
         BH_TRY(cudaEventRecord(ev[slot + 0], st));
         // zero: scalars | sort scratch (sized for this n) | scan status
         const int key_bits = 2 * root.levels + 1;   // +1: the not-in-tree sentinel 1<<2L sorts last
@@ -351,6 +367,7 @@ struct bh_engine {
             BH_TRY(cudaMemsetAsync(arrived, 0, (size_t)M * sizeof(int), st));
             const BhTreeView t = view();
             k_emit<<<grid_for(n_in, 256), 256, 0, st>>>(t, root.levels);
+            BH_RC(wait_inputs());   // bh_step_io: the masses may still be in flight
             if (climb_block) {
                 if (n_in > climb_roots_cap) {
                     dev_free(climb_roots);
@@ -373,6 +390,7 @@ struct bh_engine {
         return BH_OK;
     }
     int64_t ctr_rehomes = 0, ctr_reused = 0;
+    int io_steps_left = 0;
     bool climb_block = true;        // BH_CLIMB_BLOCK=0: per-thread global climb (k_climb)
     bool walk_lanegroup = false;     // BH_WALK_LANEGROUP=1: 4 adjacent lanes share one position (bh_walk_lanegroup)
     int walk_group_min_waves = 0;   // BH_WALK_GROUP_MIN_WAVES > 0: group walk from this many waves of 128-thread blocks per SM
@@ -487,7 +505,9 @@ struct bh_engine {
             BH_RC(evaluate(0, lo, hi));
         }
         acc_valid = false;
+        BH_RC(wait_inputs());
         BH_RC(kick(lo, hi, dtHalf, dt, 1));
+        if (io_out.armed && io_steps_left == 1) BH_RC(emit_positions_out());
         if (world > 1) vel_valid = false;
         phase = 1;
         return BH_OK;
@@ -508,6 +528,7 @@ struct bh_engine {
         if (phase != 2) return fail(BH_E_STATE, "bh_step_finish: call bh_step_end first");
         phase = 0;
         ctr.total_steps++;
+        if (io_steps_left > 0) --io_steps_left;
         if (++steps_since_rehome >= rehome_interval) rehome_due = true;
         return merge_rule();
     }
@@ -531,6 +552,27 @@ struct bh_engine {
 
 #include "bh_merge.cuh"
 #include "bh_scene.cuh"
+
+// bh_step_io: the positions are final after the last drift — send (x, y, m) to the host on the copy
+// stream while the last force evaluation runs on the compute stream
+int bh_engine::emit_positions_out() {
+    io_out.armed = false;
+    BH_TRY(cudaEventRecord(io_ev[1], st));
+    BH_TRY(cudaStreamWaitEvent(copy_st, io_ev[1], 0));
+    const double* src[3] = {x, y, m};
+    double* dst[3] = {io_out.x, io_out.y, io_out.m};
+    for (int k = 0; k < 3; ++k) {
+        if (!dst[k]) continue;
+        const double* from = src[k];
+        if (!perm_identity) {
+            k_scatter<double><<<grid_for(n, 256), 256, 0, copy_st>>>(io_stage[k], src[k], perm, (int)n);
+            ctr.kernel_launches += 1;
+            from = io_stage[k];
+        }
+        BH_TRY(cudaMemcpyAsync(dst[k], from, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, copy_st));
+    }
+    return BH_OK;
+}
 
 // fold the timers of a finished step slot into the counters (waits for that step only)
 void bh_engine::collect(EvSlot& sl) {
@@ -633,6 +675,8 @@ void bh_destroy(bh_engine* e) {
     if (e->st) cudaStreamSynchronize(e->st);
     if (e->copy_st) { cudaStreamSynchronize(e->copy_st); cudaStreamDestroy(e->copy_st); }
     for (auto& ev : e->snap_ev) if (ev) cudaEventDestroy(ev);
+    for (auto& q : e->io_stage) dev_free(q);
+    for (auto& ev : e->io_ev) if (ev) cudaEventDestroy(ev);
     dev_free(e->snap_xy); dev_free(e->snap_m);
     if (e->snap_hxy) cudaFreeHost(e->snap_hxy);
     if (e->snap_hm) cudaFreeHost(e->snap_hm);
@@ -887,6 +931,104 @@ int bh_step_finish(bh_engine* e) {
     if (e->cur->has_merge && cudaEventElapsedTime(&mg, e->ev[14], e->ev[15]) == cudaSuccess) e->ctr.ms_merge += mg;
     e->cur->has_merge = false;
     return BH_OK;
+}
+
+int bh_step_io(bh_engine* e, int32_t nsteps, int64_t n_in, const double* x_in, const double* y_in, const double* vx_in,
+               const double* vy_in, const double* m_in, int64_t cap_out, double* x_out, double* y_out, double* vx_out,
+               double* vy_out, double* m_out, int64_t* n_out) {
+    if (!e || nsteps < 0 || (x_in && (n_in < 0 || (n_in > 0 && (!y_in || !vx_in || !vy_in || !m_in)))))
+        return e ? e->fail(BH_E_ARG, "bh_step_io: bad arguments") : BH_E_ARG;
+    E_TRY(cudaSetDevice(e->device));
+    if (e->phase != 0) return e->fail(BH_E_STATE, "bh_step_io: a step is in progress");
+    const int64_t n_new = x_in ? n_in : e->n;
+    const bool want_out = x_out || y_out || vx_out || vy_out || m_out;
+    const bool merge_possible = e->par.merge_min_dist > 0.0 && n_new > 1;
+    if (merge_possible || e->world > 1 || nsteps < 1 || n_new == 0 || (want_out && cap_out < n_new)) {
+        // plain sequence (the body count may change, or there is nothing to overlap)
+        if (x_in) E_RC(bh_set_bodies(e, n_in, x_in, y_in, vx_in, vy_in, m_in));
+        E_RC(bh_step(e, nsteps));
+        if (n_out) *n_out = e->n;
+        if (want_out) return bh_get_bodies(e, cap_out, x_out, y_out, vx_out, vy_out, m_out, n_out);
+        return BH_OK;
+    }
+    if (!e->copy_st) {
+        E_TRY(cudaStreamCreateWithFlags(&e->copy_st, cudaStreamNonBlocking));
+        E_TRY(cudaEventCreateWithFlags(&e->snap_ev[0], cudaEventDisableTiming));
+        E_TRY(cudaEventCreateWithFlags(&e->snap_ev[1], cudaEventDisableTiming));
+    }
+    if (!e->io_ev[0]) {
+        E_TRY(cudaEventCreateWithFlags(&e->io_ev[0], cudaEventDisableTiming));
+        E_TRY(cudaEventCreateWithFlags(&e->io_ev[1], cudaEventDisableTiming));
+    }
+    const size_t bytes = (size_t)n_new * sizeof(double);
+    if (x_in) {
+        // ---- resetBodies: (x, y) on the compute stream, (vx, vy, m) on the copy stream
+        const bool keep_perm = (n_new == e->n && !e->perm_identity && n_new <= e->cap);
+        E_RC(e->ensure_bodies(n_new));
+        e->n = n_new;
+        if (!keep_perm) {
+            e->perm_identity = true;
+            e->rehome_due = true;
+            k_iota<<<grid_for(n_new, 256), 256, 0, e->st>>>(e->perm, (int)n_new);
+        }
+    }
+    if (n_new > e->io_cap) {
+        E_TRY(cudaStreamSynchronize(e->copy_st));
+        for (auto& q : e->io_stage) dev_free(q);
+        const int64_t c = std::max<int64_t>(n_new + n_new / 8, 1024);
+        for (auto& q : e->io_stage) E_TRY(dev_alloc(&q, (size_t)c));
+        e->io_cap = c;
+    }
+    if (x_in) {
+        E_RC(e->upload_user(e->x, x_in));
+        E_RC(e->upload_user(e->y, y_in));
+        E_TRY(cudaMemsetAsync(e->ax, 0, bytes, e->st));
+        E_TRY(cudaMemsetAsync(e->ay, 0, bytes, e->st));
+        // the copy stream must not start before the compute stream is past whatever used vx/vy/m/perm
+        E_TRY(cudaEventRecord(e->io_ev[1], e->st));
+        E_TRY(cudaStreamWaitEvent(e->copy_st, e->io_ev[1], 0));
+        const double* hin[3] = {vx_in, vy_in, m_in};
+        double* dev[3] = {e->vx, e->vy, e->m};
+        for (int k = 0; k < 3; ++k) {
+            if (e->perm_identity) {
+                E_TRY(cudaMemcpyAsync(dev[k], hin[k], bytes, cudaMemcpyHostToDevice, e->copy_st));
+            } else {
+                E_TRY(cudaMemcpyAsync(e->io_stage[k], hin[k], bytes, cudaMemcpyHostToDevice, e->copy_st));
+                k_gather<double><<<grid_for(n_new, 256), 256, 0, e->copy_st>>>(dev[k], e->io_stage[k], e->perm, (int)n_new);
+            }
+        }
+        E_TRY(cudaMemsetAsync(e->dflags, 0, sizeof(int), e->copy_st));
+        k_flag_zero_mass<<<grid_for(n_new, 256), 256, 0, e->copy_st>>>(e->m, (int)n_new, e->dflags + HF_ZERO_MASS);
+        E_TRY(cudaMemcpyAsync(e->hflags, e->dflags, sizeof(int), cudaMemcpyDeviceToHost, e->copy_st));
+        E_TRY(cudaEventRecord(e->io_ev[0], e->copy_st));
+        e->io_wait_in = true;
+        e->ctr.kernel_launches += 6;
+        e->origin_identity = true;
+        e->tree_valid = false; e->heavies_valid = false; e->vel_valid = true; e->acc_valid = false;
+    }
+    // ---- the steps; the last drift triggers the (x, y, m) read-back
+    e->io_out.x = x_out; e->io_out.y = y_out; e->io_out.m = m_out;
+    e->io_out.armed = x_out || y_out || m_out;
+    e->io_steps_left = nsteps;
+    int rc = e->run_steps(nsteps);
+    e->io_steps_left = 0;
+    e->io_out.armed = false;
+    if (rc == BH_OK && e->io_wait_in) rc = e->wait_inputs();
+    // ---- (vx, vy) after the last kick
+    if (rc == BH_OK) {
+        cudaError_t ce = cudaSuccess;
+        if (vx_out) { const int r2 = e->download_user(vx_out, (const double*)e->vx, e->dtmp); if (r2) rc = r2; }
+        if (rc == BH_OK && vy_out) {   // own staging buffer so that the two copies overlap
+            const int r2 = e->download_user(vy_out, (const double*)e->vy, e->io_stage[3]);
+            if (r2) rc = r2;
+        }
+        (void)ce;
+    }
+    cudaError_t c1 = cudaStreamSynchronize(e->st), c2 = cudaStreamSynchronize(e->copy_st);
+    if (rc == BH_OK && (c1 != cudaSuccess || c2 != cudaSuccess)) rc = e->cuda_fail(c1 != cudaSuccess ? c1 : c2, "bh_step_io");
+    if (x_in) e->any_zero_mass = e->hflags[HF_ZERO_MASS] != 0;
+    if (n_out) *n_out = e->n;
+    return rc;
 }
 
 int bh_build_tree(bh_engine* e) {

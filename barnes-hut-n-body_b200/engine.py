@@ -170,6 +170,30 @@ class NativeEngine:
     def step(self, nsteps: int = 1):
         self._check(self.lib.bh_step(self._h, nsteps), "bh_step")
 
+    def step_io(self, nsteps: int = 1, inputs=None, out=None):
+        """resetBodies(inputs); nsteps x step(); getBodies() in one call with the transfers
+        overlapped with the compute (bh_step_io).  `inputs` / `out`: 5 float64 arrays (pinned host
+        memory makes the copies asynchronous); returns the output arrays (or None)."""
+        n_in = 0
+        ins = [None] * 5
+        if inputs is not None:
+            ins = [_f64(a) for a in inputs]
+            n_in = ins[0].shape[0]
+        n_after = n_in if inputs is not None else self.n
+        outs = [None] * 5
+        if out is not None:
+            outs = list(out)
+        elif out is None and inputs is not None:
+            outs = [np.empty(n_after, np.float64) for _ in range(5)]
+        cap = outs[0].shape[0] if outs[0] is not None else 0
+        n_out = C.c_int64()
+        self._check(self.lib.bh_step_io(self._h, nsteps, n_in, *[_dp(a) for a in ins], cap, *[_dp(a) for a in outs], C.byref(n_out)),
+                    "bh_step_io")
+        if outs[0] is None:
+            return None
+        k = n_out.value
+        return tuple(a[:k] for a in outs)
+
     def compute_accelerations(self):
         n = self.n
         ax, ay = np.empty(n, np.float64), np.empty(n, np.float64)

@@ -195,6 +195,16 @@ int bh_append_uniform_random(bh_engine* e, int64_t n, double m, int32_t width_px
 /* nsteps x PhysicsEngine.step() — BarnesHutAlg.kt:405-439: build+eval, half kick,
  * drift, build+eval, half kick, merge rule (:463-532). */
 int bh_step(bh_engine* e, int32_t nsteps);
+/* resetBodies(in) ; nsteps x step() ; getBodies(out) in ONE call, so that the transfers overlap
+ * the compute: (x, y) go up first and the build starts while (vx, vy, m) are still in flight on a
+ * second stream; the final positions and masses come down while the last force evaluation runs.
+ * Same results as bh_set_bodies + bh_step + bh_get_bodies (which it falls back to when the merge
+ * rule is enabled or a multi-rank transport is set).  x_in == NULL: keep the current bodies;
+ * x_out == NULL: no read-back.  Page-locked host arrays make the copies truly asynchronous. */
+int bh_step_io(bh_engine* e, int32_t nsteps, int64_t n_in,
+               const double* x_in, const double* y_in, const double* vx_in, const double* vy_in, const double* m_in,
+               int64_t cap_out, double* x_out, double* y_out, double* vx_out, double* vy_out, double* m_out,
+               int64_t* n_out);
 /* buildTree() + computeAccelerations() on the current state, no integration —
  * BarnesHutAlg.kt:359-366 + :374-395.  The parity entry point.  ax/ay: n doubles. */
 int bh_compute_accelerations(bh_engine* e, double* ax, double* ay);

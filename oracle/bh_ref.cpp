@@ -544,6 +544,18 @@ int bh_step(bh_engine* e, int32_t nsteps) {
     return BH_OK;
 }
 
+int bh_step_io(bh_engine* e, int32_t nsteps, int64_t n_in, const double* x_in, const double* y_in, const double* vx_in,
+               const double* vy_in, const double* m_in, int64_t cap_out, double* x_out, double* y_out, double* vx_out,
+               double* vy_out, double* m_out, int64_t* n_out) {
+    if (!e) return BH_E_ARG;
+    if (x_in) { const int rc = bh_set_bodies(e, n_in, x_in, y_in, vx_in, vy_in, m_in); if (rc != BH_OK) return rc; }
+    const int rc = bh_step(e, nsteps);
+    if (rc != BH_OK) return rc;
+    if (n_out) *n_out = (int64_t)e->bodies.size();
+    if (x_out) return bh_get_bodies(e, cap_out, x_out, y_out, vx_out, vy_out, m_out, n_out);
+    return BH_OK;
+}
+
 int bh_build_tree(bh_engine* e) {
     if (!e) return BH_E_ARG;
     try { e->lastTree = e->buildTree(); }

@@ -524,3 +524,35 @@ def test_device_scene_generators_follow_bodyfactory(cuda_lib):
     e.append_disk(50_000, e.disk_params(2400, 800, kepler=1, radial_jitter=0.03, r=304.0), seed=3)
     e.step(2)
     assert e.n == len(x) + 50_000 and np.isfinite(e.get_bodies()[0]).all()
+
+
+def test_step_io_equals_set_step_get(oracle_lib, cuda_lib):
+    """bh_step_io = resetBodies + step + getBodies with overlapped transfers: bit-identical to the
+    three separate calls — first call (list order), later calls (through the home permutation,
+    incl. a re-homing step), several steps per call, merge enabled (fallback), and the oracle's."""
+    import bh_b200
+    scene = scenes.snap_f32(scenes.default_two_disks(n1=6000, n2=1500, seed=71))
+    a = bh_b200.NativeEngine(lib=cuda_lib, rehome_interval=3)
+    b = bh_b200.NativeEngine(lib=cuda_lib, rehome_interval=3)
+    for e in (a, b):
+        e.set_params(theta=0.5, merge_min_dist=0.0)
+    state = scene
+    for it in range(8):
+        k = 1 + (it % 2)
+        out = a.step_io(k, inputs=state)
+        b.set_bodies(*state)
+        b.step(k)
+        ref = b.get_bodies()
+        for u, v in zip(out, ref):
+            assert (u == v).all(), it
+        state = tuple(np.ascontiguousarray(v) for v in ref)
+    assert a.step_io(2) is None and a.n == b.n                 # no inputs, no outputs: just steps
+    b.step(2)
+    for u, v in zip(a.get_bodies(), b.get_bodies()):
+        assert (u == v).all()
+    # merge enabled: plain sequence inside, same answer as the oracle's bh_step_io
+    ms = _merge_scene(seed=72, n1=2000, n2=500)
+    g = make_engine(cuda_lib, ms, theta=0.5, merge_min_dist=8.0)
+    o = make_engine(oracle_lib, ms, theta=0.5, merge_min_dist=8.0)
+    og, oo = g.step_io(3, inputs=ms), o.step_io(3, inputs=ms)
+    assert len(og[0]) == len(oo[0]) < len(ms[0]) and (og[4] == oo[4]).all()
