@@ -26,6 +26,7 @@ _ERR_NAMES = {
 
 BH_FLAG_BODY_COUNTS = 1
 BH_FLAG_REUSE_ACC = 2
+BH_FLAG_LET = 4
 BH_COMM_ID_BYTES = 128
 BH_FIELD_POS = 0
 BH_FIELD_VEL = 1
@@ -101,6 +102,7 @@ SYMBOLS = {
     "bh_build_tree": (C.c_int, [_H]),
     "bh_get_counters": (C.c_int, [_H, C.POINTER(BhCounters)]),
     "bh_reset_counters": (C.c_int, [_H]),
+    "bh_get_let_stats": (C.c_int, [_H, _I64, C.c_int32]),
     "bh_get_body_counts": (C.c_int, [_H, _I32, _I32]),
     "bh_comm_unique_id": (C.c_int, [C.c_void_p, C.c_int32]),
     "bh_comm_init": (C.c_int, [_H, C.c_int32, C.c_int32, C.c_void_p, C.c_int32]),

@@ -15,6 +15,7 @@ struct UniqueId { char internal[128]; };   // ncclUniqueId (NCCL_UNIQUE_ID_BYTES
 typedef void* Comm;                         // ncclComm_t
 constexpr int kSuccess = 0;                 // ncclSuccess
 constexpr int kFloat64 = 8;                 // ncclFloat64
+constexpr int kSum = 0;                     // ncclSum
 
 struct Api {
     void* handle = nullptr;
@@ -22,6 +23,10 @@ struct Api {
     int (*CommInitRank)(Comm*, int, UniqueId, int) = nullptr;
     int (*CommDestroy)(Comm) = nullptr;
     int (*AllGather)(const void*, void*, size_t, int, Comm, cudaStream_t) = nullptr;
+    int (*AllReduce)(const void*, void*, size_t, int, int, Comm, cudaStream_t) = nullptr;
+    int (*Broadcast)(const void*, void*, size_t, int, int, Comm, cudaStream_t) = nullptr;
+    int (*Send)(const void*, size_t, int, int, Comm, cudaStream_t) = nullptr;
+    int (*Recv)(void*, size_t, int, int, Comm, cudaStream_t) = nullptr;
     int (*GroupStart)() = nullptr;
     int (*GroupEnd)() = nullptr;
     const char* (*GetErrorString)(int) = nullptr;
@@ -45,6 +50,10 @@ inline Api& api() {
     BH_SYM(CommInitRank, "ncclCommInitRank")
     BH_SYM(CommDestroy, "ncclCommDestroy")
     BH_SYM(AllGather, "ncclAllGather")
+    BH_SYM(AllReduce, "ncclAllReduce")
+    BH_SYM(Broadcast, "ncclBroadcast")
+    BH_SYM(Send, "ncclSend")
+    BH_SYM(Recv, "ncclRecv")
     BH_SYM(GroupStart, "ncclGroupStart")
     BH_SYM(GroupEnd, "ncclGroupEnd")
     BH_SYM(GetErrorString, "ncclGetErrorString")

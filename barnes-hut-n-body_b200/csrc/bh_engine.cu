@@ -31,6 +31,8 @@
 #include "bh_sort.cuh"
 #include "bh_kernels.cuh"
 #include "bh_comm.cuh"
+#include "bh_let_core.h"
+#include "bh_let.cuh"
 
 namespace {
 
@@ -160,6 +162,15 @@ struct bh_engine {
 
     bh_counters ctr{};
 
+    // locally-essential-tree mode (bh_let.cuh)
+    bh_let_state let;
+    bool let_usable() const;
+    bool let_ready() const;
+    int sync_positions();
+    int let_partition();
+    int let_evaluate(int slot);
+    int evaluate_slice(int slot);
+
     int fail(int code, const char* what) { err = what; return code; }
     int fail(int code, const std::string& what) { err = what; return code; }
     int cuda_fail(cudaError_t e, const char* what) {
@@ -238,7 +249,10 @@ struct bh_engine {
 
     // ---- slices ------------------------------------------------------------------------
     int64_t slice_per() const { return (n + world - 1) / world; }
-    void my_slice(int64_t* lo, int64_t* hi) const { bh_slice_bounds(n, world, rank, lo, hi); }
+    void my_slice(int64_t* lo, int64_t* hi) const {
+        if (world > 1 && let.part_valid && let.n_part == n) { *lo = let.cut[rank]; *hi = let.cut[rank + 1]; }   // cut at code boundaries
+        else bh_slice_bounds(n, world, rank, lo, hi);
+    }
 
     // ---- permutation helpers -----------------------------------------------------------
     // arr[h] <- arr[idx[h]] for the n body slots, through dtmp (pointer swap)
@@ -289,8 +303,17 @@ struct bh_engine {
         const size_t per = (size_t)slice_per();
         BH_TRY(cudaEventRecord(ev[12], st));
         int rc = A.GroupStart();
-        if (rc == bhcomm::kSuccess) rc = A.AllGather(a + (size_t)rank * per, a, per, bhcomm::kFloat64, comm, st);
-        if (rc == bhcomm::kSuccess) rc = A.AllGather(b + (size_t)rank * per, b, per, bhcomm::kFloat64, comm, st);
+        if (let.part_valid && let.n_part == n) {   // slices of different lengths: one broadcast per rank
+            for (int r = 0; r < world && rc == bhcomm::kSuccess; ++r) {
+                const size_t cnt = (size_t)(let.cut[r + 1] - let.cut[r]);
+                if (cnt == 0) continue;
+                rc = A.Broadcast(a + let.cut[r], a + let.cut[r], cnt, bhcomm::kFloat64, r, comm, st);
+                if (rc == bhcomm::kSuccess) rc = A.Broadcast(b + let.cut[r], b + let.cut[r], cnt, bhcomm::kFloat64, r, comm, st);
+            }
+        } else {
+            if (rc == bhcomm::kSuccess) rc = A.AllGather(a + (size_t)rank * per, a, per, bhcomm::kFloat64, comm, st);
+            if (rc == bhcomm::kSuccess) rc = A.AllGather(b + (size_t)rank * per, b, per, bhcomm::kFloat64, comm, st);
+        }
         const int rc2 = A.GroupEnd();
         if (rc == bhcomm::kSuccess) rc = rc2;
         if (rc != bhcomm::kSuccess) return nccl_fail(rc, "ncclAllGather");
@@ -309,12 +332,15 @@ struct bh_engine {
     }
 
     // ---- buildTree(), BH.kt:359-366 ------------------------------------------------------
-    int build(int slot = 0) {
+    int build(int slot = 0, bool timed = true) {
         tree_valid = false;
+        let.view_valid = false;
         root = BhRoot{par.root_cx, par.root_cy, par.root_half, bh_key_levels(par.root_half)};
         const int nn = (int)n;
+        if (!let.local_build) BH_RC(sync_positions());        // a replicated build needs every body's position
         if (rehome_due && nn > 0) { BH_RC(sync_velocities()); BH_RC(wait_inputs()); }
-        BH_TRY(cudaEventRecord(ev[slot + 0], st));
+        if (timed) BH_TRY(cudaEventRecord(ev[slot + 0], st));
+        bool rehomed = false;
         // zero: scalars | sort scratch (sized for this n) | scan status
         const int key_bits = 2 * root.levels + 1;   // +1: the not-in-tree sentinel 1<<2L sorts last
         const int passes = (key_bits + bhsort::RADIX_BITS - 1) / bhsort::RADIX_BITS;
@@ -324,7 +350,11 @@ struct bh_engine {
         n_in = 0; n_internal = 0; M = 0;
         if (nn > 0) {
             const uint64_t sentinel = 1ull << (2 * root.levels);
-            k_keygen<<<std::min(grid_for(nn, 256), num_sms * 16), 256, 0, st>>>(x, y, nn, root, bh_make_grid(root), sentinel, keys_a, sc());
+            if (let.local_build)
+                k_keygen<<<std::min(grid_for(nn, 256), num_sms * 16), 256, 0, st>>>(x, y, nn, root, bh_make_grid(root), sentinel, keys_a, sc(),
+                                                                                      let.ell, let.split.cs[rank], let.split.cs[rank + 1]);
+            else
+                k_keygen<<<std::min(grid_for(nn, 256), num_sms * 16), 256, 0, st>>>(x, y, nn, root, bh_make_grid(root), sentinel, keys_a, sc());
             const int where = sort_pairs(nn, key_bits);
             keys_sorted = where ? keys_b : keys_a;
             int* ord = reinterpret_cast<int*>(where ? vals_b : vals_a);
@@ -342,6 +372,7 @@ struct bh_engine {
                 rehome_due = false;
                 steps_since_rehome = 0;
                 ctr_rehomes++;
+                rehomed = true;
             }
             k_count_scan<<<grid_for(nn, SCAN_TILE), SCAN_THREADS, 0, st>>>(keys_sorted, root.levels, sc(), S, scan_status);
             ctr.kernel_launches += 1;
@@ -353,6 +384,7 @@ struct bh_engine {
         ctr.n_in_tree = n_in; ctr.n_out_of_box = n - n_in; ctr.n_internal = n_internal; ctr.n_cells = M;
         ctr.n_jitter_bodies = sc_host->n_jitter; ctr.max_depth = sc_host->max_depth; ctr.key_levels = root.levels;
         BH_RC(ensure_cells((int64_t)M + 1));   // + the terminal record the walk idles on
+        if (rehomed && let_usable()) BH_RC(let_partition());   // slices of the new home order, cut at code boundaries
         jitter_active = false;
         if (sc_host->n_jitter > 0) {
             // jitter regime (BH.kt:145-156): replay each cluster of equal keys sequentially; this
@@ -384,7 +416,7 @@ struct bh_engine {
                 k_climb<<<grid_for(n_in, 256), 256, 0, st>>>(t, root, x, y, m, jitter_active ? jflag : nullptr, leafpos);
             ctr.kernel_launches += 2;
         }
-        BH_TRY(cudaEventRecord(ev[slot + 1], st));
+        if (timed) BH_TRY(cudaEventRecord(ev[slot + 1], st));
         BH_TRY(cudaGetLastError());
         tree_valid = true;
         return BH_OK;
@@ -421,7 +453,8 @@ struct bh_engine {
     }
 
     // computeAccelerations(root), BH.kt:374-395, for the home slots [first, first+count)
-    int walk(int64_t first, int64_t count, int slot = 0) {
+    int walk(int64_t first, int64_t count, int slot = 0, const BhTreeView* over = nullptr) {
+        const BhTreeView tv = over ? *over : view();
         BH_TRY(cudaEventRecord(ev[slot + 2], st));
         if (count > 0) {
             const BhWalkParams w = bh_walk_params(par.theta, par.soft2, par.root_half);
@@ -430,15 +463,15 @@ struct bh_engine {
             if (walk_group_min_waves > 0 && count >= (int64_t)num_sms * 128 * WALK_G * walk_group_min_waves) {
                 const int g = grid_for((count + WALK_G - 1) / WALK_G, 128);
                 if (any_zero_mass)
-                    k_walk_group<true><<<g, 128, 0, st>>>(view(), w, (int)first, (int)count, x, y, m, leafpos, par.G, ax, ay, cntI, cntO, sc(), tot);
+                    k_walk_group<true><<<g, 128, 0, st>>>(tv, w, (int)first, (int)count, x, y, m, leafpos, par.G, ax, ay, cntI, cntO, sc(), tot);
                 else
-                    k_walk_group<false><<<g, 128, 0, st>>>(view(), w, (int)first, (int)count, x, y, m, leafpos, par.G, ax, ay, cntI, cntO, sc(), tot);
+                    k_walk_group<false><<<g, 128, 0, st>>>(tv, w, (int)first, (int)count, x, y, m, leafpos, par.G, ax, ay, cntI, cntO, sc(), tot);
             } else if (walk_lanegroup) {
                 const int g = grid_for(count, 128);
-                k_walk_lanegroup<<<g, 128, 0, st>>>(view(), w, (int)first, (int)count, x, y, m, leafpos, par.G, ax, ay, cntI, cntO, sc(), tot);
+                k_walk_lanegroup<<<g, 128, 0, st>>>(tv, w, (int)first, (int)count, x, y, m, leafpos, par.G, ax, ay, cntI, cntO, sc(), tot);
             } else {
                 const int g = grid_for(count, 128);
-                k_walk<<<g, 128, 0, st>>>(view(), w, (int)first, (int)count, x, y, m, leafpos, par.G, ax, ay, cntI, cntO, sc(), tot);
+                k_walk<<<g, 128, 0, st>>>(tv, w, (int)first, (int)count, x, y, m, leafpos, par.G, ax, ay, cntI, cntO, sc(), tot);
             }
             ctr.kernel_launches += 1;
         }
@@ -502,7 +535,8 @@ struct bh_engine {
             BH_TRY(cudaEventRecord(ev[2], st)); BH_TRY(cudaEventRecord(ev[3], st));
             ctr_reused++;
         } else {
-            BH_RC(evaluate(0, lo, hi));
+            BH_RC(evaluate_slice(0));
+            my_slice(&lo, &hi);          // a re-homing build may have re-cut the slices
         }
         acc_valid = false;
         BH_RC(wait_inputs());
@@ -516,8 +550,8 @@ struct bh_engine {
         if (phase != 1) return fail(BH_E_STATE, "bh_step_end: call bh_step_begin (and exchange BH_FIELD_POS) first");
         const double dt = par.dt, dtHalf = par.dt * 0.5;
         int64_t lo, hi;
+        BH_RC(evaluate_slice(4));
         my_slice(&lo, &hi);
-        BH_RC(evaluate(4, lo, hi));
         BH_RC(kick(lo, hi, dtHalf, dt, 0));
         acc_valid = !jitter_active;      // a jittering build mutated positions: the next build will again
         acc_par = par;
@@ -535,7 +569,12 @@ struct bh_engine {
     // one whole step with the engine's own transport
     int step_once() {
         BH_RC(step_begin());
-        if (world > 1) BH_RC(all_gather_pair(x, y));      // the one exchange of the step: drifted positions
+        // the one exchange of the step: drifted positions — not in domain mode, where every rank keeps
+        // only its own slice current and the next build exchanges strays and tree blocks instead
+        if (world > 1) {
+            if (let_usable()) let.pos_valid = false;
+            else BH_RC(all_gather_pair(x, y));
+        }
         BH_RC(step_end());
         return step_finish();
     }
@@ -552,6 +591,35 @@ struct bh_engine {
 
 #include "bh_merge.cuh"
 #include "bh_scene.cuh"
+#include "bh_let_engine.cuh"
+
+// one force evaluation for this rank's slice: over the locally essential tree when the domain mode is
+// active, else over the (replicated) tree of all bodies
+int bh_engine::evaluate_slice(int slot) {
+    if (let_usable()) {
+        if (!let_ready()) {
+            if (let.n_declined != n) rehome_due = true;       // (re)partition through a re-homing build
+        } else {
+            const int rc = let_evaluate(slot);
+            if (rc == BH_OK) {
+                BhTreeView lv{};
+                lv.cell = let.cell; lv.cd = let.cd; lv.sk = let.sk; lv.arrived = let.arrived; lv.n_in = let.n_items; lv.M = let.M;
+                BH_RC(walk(let.cut[rank], let.cut[rank + 1] - let.cut[rank], slot, &lv));
+                ctr.total_evaluations++;
+                return BH_OK;
+            }
+            if (rc != BH_LET_RETRY) return rc;
+            let.fallbacks++;
+            rehome_due = true;
+        }
+    }
+    BH_RC(build(slot));
+    int64_t lo, hi;
+    my_slice(&lo, &hi);
+    BH_RC(walk(lo, hi - lo, slot));
+    ctr.total_evaluations++;
+    return BH_OK;
+}
 
 // bh_step_io: the positions are final after the last drift — send (x, y, m) to the host on the copy
 // stream while the last force evaluation runs on the compute stream
@@ -683,6 +751,7 @@ void bh_destroy(bh_engine* e) {
     if (e->comm && bhcomm::api().ok) bhcomm::api().CommDestroy(e->comm);
     e->free_bodies();
     e->free_cells();
+    e->let.release();
     dev_free(e->tot); dev_free(e->red); dev_free(e->dflags); dev_free(e->heavy);
     if (e->sc_host) cudaFreeHost(e->sc_host);
     if (e->tot_host) cudaFreeHost(e->tot_host);
@@ -753,6 +822,9 @@ int bh_set_bodies(bh_engine* e, int64_t n, const double* x, const double* y, con
     e->heavies_valid = false;
     e->vel_valid = true;
     e->acc_valid = false;
+    e->let.pos_valid = true;
+    e->let.part_valid = false; e->let.n_declined = -1;
+    if (e->let.enabled) e->rehome_due = true;
     return BH_OK;
 }
 
@@ -764,6 +836,7 @@ int bh_get_bodies(bh_engine* e, int64_t cap, double* x, double* y, double* vx, d
     if (cap < e->n) return e->fail(BH_E_ARG, "bh_get_bodies: capacity too small");
     E_TRY(cudaSetDevice(e->device));
     if (e->n > 0) {
+        E_RC(e->sync_positions());
         if (vx || vy) E_RC(e->sync_velocities());
         // one staging buffer: each scatter is stream-ordered behind the previous copy
         E_RC(e->download_user(x, e->x, e->dtmp)); E_RC(e->download_user(y, e->y, e->dtmp));
@@ -792,6 +865,7 @@ int bh_get_positions_f32(bh_engine* e, int64_t cap, float* xy, float* m, int64_t
     if (cap < e->n) return e->fail(BH_E_ARG, "bh_get_positions_f32: capacity too small");
     if (e->n == 0) return BH_OK;
     E_TRY(cudaSetDevice(e->device));
+    E_RC(e->sync_positions());
     // staged in user order through dtmp (float2[n]) and itmp (float[n])
     float2* dxy = reinterpret_cast<float2*>(e->dtmp);
     float* dm = reinterpret_cast<float*>(e->itmp);
@@ -821,6 +895,7 @@ int bh_append_disk(bh_engine* e, int64_t n_total, const bh_disk_params* p, uint6
     E_TRY(cudaSetDevice(e->device));
     const int64_t add = std::max<int64_t>(n_total, 1);   // sats = (nTotal - 1).coerceAtLeast(0), plus the centre
     if (e->n + add >= (int64_t)1 << 30) return e->fail(BH_E_ARG, "more than 2^30 bodies are not supported");
+    E_RC(e->sync_positions());
     E_RC(e->sync_velocities());
     E_RC(e->grow_keep(add));
     const int64_t b = e->n;
@@ -843,6 +918,7 @@ int bh_append_uniform_random(bh_engine* e, int64_t n, double m, int32_t w, int32
     if (n <= 0 || !(m > 0.0)) return BH_OK;              // BodyFactory.kt:165: empty list
     E_TRY(cudaSetDevice(e->device));
     if (e->n + n >= (int64_t)1 << 30) return e->fail(BH_E_ARG, "more than 2^30 bodies are not supported");
+    E_RC(e->sync_positions());
     E_RC(e->sync_velocities());
     E_RC(e->grow_keep(n));
     const int64_t b = e->n;
@@ -874,6 +950,7 @@ int bh_request_positions_f32(bh_engine* e) {
     }
     if (e->snap_n >= 0) E_TRY(cudaStreamWaitEvent(e->st, e->snap_ev[1], 0));   // previous copy still reads the staging
     e->snap_n = e->n;
+    E_RC(e->sync_positions());
     if (e->n > 0) {
         k_positions_f32<<<grid_for(e->n, 256), 256, 0, e->st>>>(e->x, e->y, e->m, e->perm, (int)e->n, e->snap_xy, e->snap_m);
         e->ctr.kernel_launches += 1;
@@ -1056,6 +1133,7 @@ int bh_direct_sum(bh_engine* e, double* ax, double* ay) {
     if (!e) return BH_E_ARG;
     E_TRY(cudaSetDevice(e->device));
     if (e->n == 0) return BH_OK;
+    E_RC(e->sync_positions());
     // results go to the sort buffers (not e->ax/ay, which belong to the integrator)
     double* dax = reinterpret_cast<double*>(e->keys_a);
     double* day = reinterpret_cast<double*>(e->keys_b);
@@ -1074,6 +1152,7 @@ int bh_energy(bh_engine* e, double* ke, double* pe, double* px, double* py) {
     E_TRY(cudaSetDevice(e->device));
     double h[4] = {0, 0, 0, 0};
     if (e->n > 0) {
+        E_RC(e->sync_positions());
         E_RC(e->sync_velocities());
         E_TRY(cudaMemsetAsync(e->red, 0, 4 * sizeof(double), e->st));
         k_energy<<<grid_for(e->n, DS_TILE), DS_TILE, 0, e->st>>>(e->x, e->y, e->vx, e->vy, e->m, (int)e->n, e->par.soft2, e->red);
@@ -1267,6 +1346,11 @@ int bh_comm_init(bh_engine* e, int32_t rank, int32_t world, const void* id, int3
     const int rc = A.CommInitRank(&e->comm, world, uid, rank);
     if (rc != bhcomm::kSuccess) return e->nccl_fail(rc, "ncclCommInitRank");
     e->rank = rank; e->world = world; e->transport = bh_engine::T_NCCL;
+    // domain mode: BH_FLAG_LET, or BH_LET=1/0 in the environment (overrides the flag)
+    e->let.enabled = (e->cfg.flags & BH_FLAG_LET) != 0;
+    if (const char* s = getenv("BH_LET")) e->let.enabled = atoi(s) != 0;
+    if (world > 16) e->let.enabled = false;
+    if (e->let.enabled) e->rehome_due = true;
     return BH_OK;
 }
 
@@ -1309,6 +1393,14 @@ int bh_import_slices(bh_engine* e, int32_t field, int64_t n, const double* a, co
     E_TRY(cudaStreamSynchronize(e->st));
     if (field == BH_FIELD_VEL) e->vel_valid = true;
     else { e->tree_valid = false; e->acc_valid = false; }
+    return BH_OK;
+}
+
+int bh_get_let_stats(bh_engine* e, int64_t* out, int32_t n_out) {
+    if (!e || !out || n_out < 1) return BH_E_ARG;
+    const int64_t v[10] = {e->let.enabled ? 1 : 0, e->let.part_valid ? 1 : 0, e->let.ell, e->let.evaluations, e->let.fallbacks,
+                           e->let.M, e->let.last_imported, e->let.last_sent, e->let.last_strays, e->let.n_items};
+    for (int k = 0; k < n_out && k < 10; ++k) out[k] = v[k];
     return BH_OK;
 }
 

@@ -73,14 +73,19 @@ __device__ __forceinline__ int bh_tile_lookback(uint32_t* __restrict__ status, i
 // HBM-bound: 16 B read + 8 B written per body.
 __global__ void __launch_bounds__(256) k_keygen(const double* __restrict__ x, const double* __restrict__ y, int n,
                                                 BhRoot root, BhGrid grid, uint64_t sentinel, uint64_t* __restrict__ keys,
-                                                DevScalars* __restrict__ sc) {
+                                                DevScalars* __restrict__ sc, int ell = -1, uint32_t c_lo = 0, uint32_t c_hi = 0) {
     // grid-stride: ONE atomic per block for the in-box count (same-address atomics serialise in L2)
     int cnt = 0;
     for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < n; b += gridDim.x * blockDim.x) {
         const double px = x[b], py = y[b];
-        const bool in = bh_root_contains(root, px, py);
+        bool in = bh_root_contains(root, px, py);
         // closed form on the exact grid when the root box allows it, else the literal descent
-        keys[b] = in ? (grid.exact ? bh_morton_key_grid(grid, root.levels, px, py) : bh_morton_key(root, px, py)) : sentinel;
+        uint64_t key = in ? (grid.exact ? bh_morton_key_grid(grid, root.levels, px, py) : bh_morton_key(root, px, py)) : sentinel;
+        if (ell >= 0 && in) {   // locally essential tree: only the bodies of this rank's code range enter its tree
+            const uint32_t c = (uint32_t)(key >> (2 * (root.levels - ell)));
+            if (c < c_lo || c >= c_hi) { in = false; key = sentinel; }
+        }
+        keys[b] = key;
         cnt += in;
     }
     if (sc) {

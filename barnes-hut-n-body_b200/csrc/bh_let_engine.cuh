@@ -1,0 +1,214 @@
+// bh_let_engine.cuh — bh_engine methods of the locally-essential-tree mode (see bh_let.cuh).
+#ifndef BH_LET_ENGINE_CUH
+#define BH_LET_ENGINE_CUH
+
+#define LET_GROW(field, need) BH_TRY(let_grow(let.field, let.field##_cap, (int64_t)(need)))
+
+inline bool bh_engine::let_usable() const {
+    return let.enabled && world > 1 && world <= 16 && transport == T_NCCL && !merge_enabled();
+}
+inline bool bh_engine::let_ready() const {
+    return let_usable() && let.part_valid && let.n_part == n && !rehome_due && let.part_root.cx == par.root_cx &&
+           let.part_root.cy == par.root_cy && let.part_root.half == par.root_half;
+}
+
+// every rank needs every body's position (replicated build, read-back, diagnostics)
+inline int bh_engine::sync_positions() {
+    if (let.pos_valid || world <= 1) { let.pos_valid = true; return BH_OK; }
+    if (transport != T_NCCL) return fail(BH_E_STATE, "positions are not replicated");
+    BH_RC(all_gather_pair(x, y));
+    let.pos_valid = true;
+    return BH_OK;
+}
+
+// After a re-homing build (home order = global Morton order, replicated): cut the slices at code
+// boundaries.  Every rank computes the same cuts from the same keys.
+inline int bh_engine::let_partition() {
+    let.part_valid = false;
+    const int ell = bh_let_choose_ell((long long)n, root.levels);
+    let.n_declined = n;
+    if (ell < 1 || n_in < 2 * world) return BH_OK;      // too small / too shallow: stay replicated
+    let.ell = ell;
+    let.lam = bh_let_lambda(ell);
+    let.ncodes = 1u << (2 * ell);
+    let.bw = (int)std::max<int64_t>(1, ((int64_t)1 << (2 * let.lam)) / 64);
+    if (!let.dcnt) {
+        BH_TRY(cudaMalloc((void**)&let.dcnt, 16 * sizeof(int)));
+        BH_TRY(cudaMalloc((void**)&let.dcollect, 64 * sizeof(int)));
+        BH_TRY(cudaMallocHost((void**)&let.hcollect, 64 * sizeof(int)));
+        BH_TRY(cudaMallocHost((void**)&let.hhdr, 2 * 17 * sizeof(double)));
+        BH_TRY(cudaMallocHost((void**)&let.hcut, 64 * sizeof(int)));
+    }
+    k_let_cut<<<1, 32, 0, st>>>(keys_sorted, n_in, (int)n, root.levels, ell, world, let.dcollect);
+    ctr.kernel_launches += 1;
+    BH_TRY(cudaMemcpyAsync(let.hcut, let.dcollect, 34 * sizeof(int), cudaMemcpyDeviceToHost, st));
+    BH_TRY(cudaStreamSynchronize(st));
+    BH_TRY(cudaGetLastError());
+    let.split.world = world; let.split.me = rank;
+    for (int r = 0; r <= world; ++r) { let.cut[r] = let.hcut[r]; let.split.cs[r] = (uint32_t)let.hcut[17 + r]; }
+    for (int r = 0; r < world; ++r) if (let.cut[r + 1] < let.cut[r]) return BH_OK;
+    let.stray_cap = std::max<int64_t>(1024, n / world / 16);
+    let.seg_len = LET_SEG_HDR + let.bw + 4 * let.stray_cap;
+    let.part_root = root;
+    let.n_part = n;
+    let.part_valid = true;
+    let.n_declined = -1;
+    return BH_OK;
+}
+
+// One force evaluation over the locally essential tree.  Returns BH_LET_RETRY when the evaluation
+// has to be redone after a re-homing (stray overflow, or a stray inside a jitter cluster).
+constexpr int BH_LET_RETRY = 1;
+inline int bh_engine::let_evaluate(int slot) {
+    bhcomm::Api& A = bhcomm::api();
+    const int64_t lo = let.cut[rank], hi = let.cut[rank + 1];
+    const int n_own = (int)(hi - lo);
+    const int ell = let.ell, P = world;
+    const uint32_t ncodes = let.ncodes, c_lo = let.split.cs[rank], c_hi = let.split.cs[rank + 1], mylen = c_hi - c_lo;
+    const int cap = (int)let.stray_cap;
+    root = BhRoot{par.root_cx, par.root_cy, par.root_half, bh_key_levels(par.root_half)};
+    const BhGrid grid = bh_make_grid(root);
+    BH_TRY(cudaEventRecord(ev[slot + 0], st));
+
+    // ---- 1. local arrays, footprint, strays
+    const int64_t nl_max = (int64_t)n_own + (int64_t)(P - 1) * cap;
+    LET_GROW(lx, nl_max + PAD); LET_GROW(ly, nl_max + PAD); LET_GROW(lm, nl_max + PAD);
+    LET_GROW(lperm, nl_max + PAD); LET_GROW(lleaf, nl_max + PAD);
+    LET_GROW(segs, let.seg_len * P);
+    double* myseg = let.segs + (size_t)rank * let.seg_len;
+    k_let_seg_init<<<grid_for(LET_SEG_HDR + let.bw, 256), 256, 0, st>>>(myseg, let.bw, let.dcnt);
+    if (n_own > 0)
+        k_let_local<<<grid_for(n_own, 256), 256, 0, st>>>(n_own, x + lo, y + lo, m + lo, perm + lo, root, grid, ell, let.lam, c_lo, c_hi,
+                                                            cap, let.lx, let.ly, let.lm, let.lperm, myseg, let.bw, let.dcnt);
+    k_let_seg_header<<<1, 1, 0, st>>>(myseg, let.dcnt, cap);
+    ctr.kernel_launches += 3;
+    int rc = A.AllGather(myseg, let.segs, (size_t)let.seg_len, bhcomm::kFloat64, comm, st);
+    if (rc != bhcomm::kSuccess) return nccl_fail(rc, "ncclAllGather(segments)");
+    BH_TRY(cudaMemcpy2DAsync(let.hhdr, 2 * sizeof(double), let.segs, (size_t)let.seg_len * sizeof(double), 2 * sizeof(double), (size_t)P,
+                             cudaMemcpyDeviceToHost, st));
+    BH_TRY(cudaStreamSynchronize(st));
+    int64_t others = 0, strays_all = 0;
+    bool overflow = false;
+    for (int q = 0; q < P; ++q) {
+        strays_all += (int64_t)let.hhdr[2 * q];
+        if (q != rank) others += (int64_t)let.hhdr[2 * q];
+        overflow |= let.hhdr[2 * q + 1] != 0.0;
+    }
+    if (overflow) return BH_LET_RETRY;
+    let.last_strays = (int64_t)let.hhdr[2 * rank];
+    // ---- 2. guests
+    const int n_loc = n_own + (int)others;
+    if (others > 0) {
+        BH_TRY(cudaMemsetAsync(let.lx + n_own, 0xFF, (size_t)others * sizeof(double), st));   // NaN: outside the root box
+        BH_TRY(cudaMemsetAsync(let.ly + n_own, 0xFF, (size_t)others * sizeof(double), st));
+        BH_TRY(cudaMemsetAsync(let.lm + n_own, 0, (size_t)others * sizeof(double), st));
+        BH_TRY(cudaMemsetAsync(let.lperm + n_own, 0, (size_t)others * sizeof(int), st));
+        k_let_guests<<<grid_for((int64_t)P * cap, 256), 256, 0, st>>>(let.segs, let.seg_len, let.bw, cap, P, rank, root, grid, ell, c_lo, c_hi,
+                                                                       n_own, (int)others, let.lx, let.ly, let.lm, let.lperm, let.dcnt);
+        ctr.kernel_launches += 1;
+    }
+    // ---- 3. the single-GPU build on the local arrays (keys outside [c_lo, c_hi) -> not in the tree)
+    {
+        double *sx = x, *sy = y, *sm = m;
+        int *sperm = perm, *sleaf = leafpos;
+        const int64_t sn = n;
+        x = let.lx; y = let.ly; m = let.lm; perm = let.lperm; leafpos = let.lleaf; n = n_loc;
+        let.local_build = true;
+        const int brc = build(slot, false);
+        let.local_build = false;
+        x = sx; y = sy; m = sm; perm = sperm; leafpos = sleaf; n = sn;
+        BH_RC(brc);
+    }
+    tree_valid = false;              // the engine's cell arrays hold the LOCAL tree: exports rebuild the global one
+    const bool jit = jitter_active;
+    if (jit && n_in > 0) {
+        k_let_jitter_check<<<grid_for(n_in, 256), 256, 0, st>>>(keys_sorted, order, n_in, n_own, let.dcnt + LET_D_FLAG);
+        ctr.kernel_launches += 1;
+    }
+    // ---- 4. level-ELL summaries -> replicated table (the P extra entries carry the ranks' retry flags)
+    LET_GROW(table, ncodes + 17);
+    BH_TRY(cudaMemsetAsync(let.table, 0, (size_t)(ncodes + P) * sizeof(BhLetEntry), st));
+    if (n_in > 0) {
+        k_let_summary<<<grid_for(n_in, 256), 256, 0, st>>>(view(), root.levels, ell, let.lx, let.ly, let.lm, jit ? jflag : nullptr, let.table);
+        ctr.kernel_launches += 1;
+    }
+    k_let_flag<<<1, 1, 0, st>>>(let.table + ncodes + rank, let.dcnt + LET_D_FLAG);
+    rc = A.AllReduce(let.table, let.table, (size_t)(ncodes + P) * 6, bhcomm::kFloat64, bhcomm::kSum, comm, st);
+    if (rc != bhcomm::kSuccess) return nccl_fail(rc, "ncclAllReduce(table)");
+    // ---- 5. plan
+    const int n_slots = 2 * (int)ncodes;
+    LET_GROW(nit, ncodes + 1); LET_GROW(blk, ncodes + 1); LET_GROW(recvsz, ncodes + 1); LET_GROW(recvoff, ncodes + 2);
+    LET_GROW(item_first, ncodes + 2); LET_GROW(dst, ncodes + 1);
+    LET_GROW(sendsz, (int64_t)P * mylen + 1); LET_GROW(sendoff, (int64_t)P * mylen + 2);
+    LET_GROW(ikey, n_slots + 1); LET_GROW(itype, n_slots + 1); LET_GROW(iw, n_slots + 1); LET_GROW(icnt, n_slots + 1);
+    LET_GROW(iS, n_slots + 2); LET_GROW(iW, n_slots + 2); LET_GROW(ilp, n_slots + 1);
+    const double theta2 = par.theta * par.theta;
+    k_let_plan<<<grid_for(ncodes, 256), 256, 0, st>>>(let.table, ncodes, let.segs, let.seg_len, let.split, theta2, par.soft2, root, ell,
+                                                        let.nit, let.blk, let.recvsz, let.sendsz);
+    BH_RC(excl_scan(let.nit, (int)ncodes, let.item_first));
+    BH_RC(excl_scan(let.recvsz, (int)ncodes, let.recvoff));
+    BH_RC(excl_scan(let.sendsz, (int)(P * mylen), let.sendoff));
+    k_let_items<<<grid_for(ncodes, 256), 256, 0, st>>>(ncodes, let.item_first, let.blk, root.levels, ell, let.ikey, let.itype, let.iw);
+    k_let_item_cnt<<<grid_for(n_slots, 256), 256, 0, st>>>(let.ikey, let.item_first + ncodes, n_slots, root.levels, let.icnt, let.iw);
+    BH_RC(excl_scan(let.icnt, n_slots, let.iS));
+    BH_RC(excl_scan(let.iw, n_slots, let.iW));
+    k_let_collect<<<1, 32, 0, st>>>(let.item_first, ncodes, let.iS, let.iW, let.recvoff, let.sendoff, let.split, let.dcollect);
+    ctr.kernel_launches += 5;
+    BH_TRY(cudaMemcpyAsync(let.hcollect, let.dcollect, 40 * sizeof(int), cudaMemcpyDeviceToHost, st));
+    BH_TRY(cudaMemcpy2DAsync(let.hhdr, sizeof(double), let.table + ncodes, sizeof(BhLetEntry), sizeof(double), (size_t)P,
+                             cudaMemcpyDeviceToHost, st));
+    BH_TRY(cudaStreamSynchronize(st));
+    BH_TRY(cudaGetLastError());
+    for (int q = 0; q < P; ++q) if (let.hhdr[q] != 0.0) return BH_LET_RETRY;   // a stray sits in a jitter cluster of its host
+    let.n_items = let.hcollect[0];
+    let.M = let.hcollect[1];
+    const int* roff = let.hcollect + 2;
+    const int* soff = let.hcollect + 2 + 17;
+    if (jit && n_own > 0) {          // the jitter replay mutated own bodies (BH.kt:145-156): keep the mutation
+        BH_TRY(cudaMemcpyAsync(x + lo, let.lx, (size_t)n_own * sizeof(double), cudaMemcpyDeviceToDevice, st));
+        BH_TRY(cudaMemcpyAsync(y + lo, let.ly, (size_t)n_own * sizeof(double), cudaMemcpyDeviceToDevice, st));
+        let.pos_valid = false;
+    }
+    // ---- 6. blocks to the ranks that may open them
+    LET_GROW(sendbuf, (std::max(1, soff[P]))); LET_GROW(recvbuf, (std::max(1, roff[P])));
+    LET_GROW(cell, (int64_t)let.M + 1); LET_GROW(cd, (int64_t)let.M + 1); LET_GROW(sk, (int64_t)let.M + 1); LET_GROW(arrived, (int64_t)let.M + 1);
+    if (soff[P] > 0) {
+        k_let_pack<<<grid_for((int64_t)P * mylen * 32, 256), 256, 0, st>>>(let.table, let.split, let.sendsz, let.sendoff, cd, sk, let.sendbuf);
+        ctr.kernel_launches += 1;
+    }
+    rc = A.GroupStart();
+    for (int q = 0; q < P && rc == bhcomm::kSuccess; ++q) {
+        if (q == rank) continue;
+        const int ns = soff[q + 1] - soff[q], nr = roff[q + 1] - roff[q];
+        if (ns > 0) rc = A.Send(let.sendbuf + soff[q], (size_t)ns * 4, bhcomm::kFloat64, q, comm, st);
+        if (nr > 0 && rc == bhcomm::kSuccess) rc = A.Recv(let.recvbuf + roff[q], (size_t)nr * 4, bhcomm::kFloat64, q, comm, st);
+    }
+    const int rc2 = A.GroupEnd();
+    if (rc == bhcomm::kSuccess) rc = rc2;
+    if (rc != bhcomm::kSuccess) return nccl_fail(rc, "ncclSend/ncclRecv(blocks)");
+    let.last_imported = roff[P]; let.last_sent = soff[P];
+    // ---- 7. top tree + blocks + exact climb
+    BhTreeView lv{};
+    lv.cell = let.cell; lv.cd = let.cd; lv.sk = let.sk; lv.arrived = let.arrived; lv.n_in = let.n_items; lv.M = let.M;
+    const BhLetItems it{let.ikey, let.itype, let.iS, let.iW, let.n_items};
+    BH_TRY(cudaMemsetAsync(let.arrived, 0, (size_t)(let.M + 1) * sizeof(int), st));
+    BH_TRY(cudaMemsetAsync(let.dst, 0xFF, (size_t)ncodes * sizeof(int), st));
+    if (let.n_items > 0) {
+        k_let_emit<<<grid_for(let.n_items, 256), 256, 0, st>>>(it, let.sk, root.levels, ell, let.ilp, let.dst);
+        k_let_blocks<<<grid_for((int64_t)ncodes * 32, 256), 256, 0, st>>>(lv, let.table, ncodes, let.split, let.nit, let.blk, let.dst, let.recvoff,
+                                                                          let.recvbuf, cd, sk, root.half);
+    }
+    k_let_climb<<<std::max(1, grid_for(let.n_items, 128)), 128, 0, st>>>(lv, root, it, let.table, root.levels, ell, let.ilp);
+    if (n_own > 0)
+        k_let_leafpos<<<grid_for(n_own, 256), 256, 0, st>>>(n_own, let.lleaf, let.lx, let.ly, root, grid, ell, let.table, let.dst, let.blk, lv, leafpos + lo);
+    ctr.kernel_launches += 4;
+    BH_TRY(cudaEventRecord(ev[slot + 1], st));
+    BH_TRY(cudaGetLastError());
+    ctr.n_cells = let.M;
+    let.view_valid = true;
+    let.evaluations++;
+    return BH_OK;
+}
+
+#undef LET_GROW
+#endif  // BH_LET_ENGINE_CUH

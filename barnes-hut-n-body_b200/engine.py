@@ -269,6 +269,14 @@ class NativeEngine:
         self._check(self.lib.bh_get_body_counts(self._h, _ip(i), _ip(o)), "bh_get_body_counts")
         return i, o
 
+    def let_stats(self) -> dict:
+        """Domain-mode (BH_FLAG_LET) statistics of the last evaluation on this rank."""
+        v = np.zeros(10, np.int64)
+        self._check(self.lib.bh_get_let_stats(self._h, v.ctypes.data_as(C.POINTER(C.c_int64)), 10), "bh_get_let_stats")
+        names = ("enabled", "partition_valid", "cut_level", "let_evaluations", "fallbacks", "let_cells", "cells_imported",
+                 "cells_sent", "own_strays", "top_items")
+        return {k: int(x) for k, x in zip(names, v)}
+
     # -- multi-GPU --------------------------------------------------------------------
     def comm_unique_id(self) -> bytes:
         buf = C.create_string_buffer(_abi.BH_COMM_ID_BYTES)

@@ -180,7 +180,8 @@ def main():
 
     scene, W, H = workload(n_gpus, args.bodies)
     n = len(scene[0])
-    eng = bh_b200.NativeEngine(device=local_rank, capacity_hint=n)
+    # N > 1: domain mode (BH_FLAG_LET) — every rank builds its own Morton range and walks a locally essential tree
+    eng = bh_b200.NativeEngine(device=local_rank, capacity_hint=n, flags=bh_b200.BH_FLAG_LET if world > 1 else 0)
     eng.set_window(W, H)
     eng.set_params(theta=THETA, merge_min_dist=0.0)
     if world > 1:
@@ -200,6 +201,7 @@ def main():
     wall = time.perf_counter() - t0
     clocks = sampler.stop()
     c = eng.counters()
+    let_stats = eng.let_stats() if world > 1 else None
     dev_ms = allmax(c["ms_step_call"])              # CUDA events on the engine's stream, max over ranks
     wall = allmax(wall)
     inter = allsum(float(c["total_interactions"]))
@@ -326,13 +328,18 @@ def main():
             "dtype": "f32 interactions, f64 state/COM/integrator", "data": "synthetic",
             "config": {"workload": f"{n}-body uniform 'C' cloud ({args.bodies}/GPU), theta={THETA}, {W}x{H} window, G=80, dt=0.005, merge off",
                        "step": "PhysicsEngine.step(): 2 builds + 2 evaluations + KDK",
-                       "parallelism": "single GPU" if n_gpus == 1 else f"replicated tree, {n_gpus} Morton slices of targets, NCCL all-gather of positions",
+                       "parallelism": "single GPU" if n_gpus == 1 else (
+                           f"domain mode: {n_gpus} Morton ranges, local tree per rank + locally essential tree (all-reduced level summaries, "
+                           f"boundary subtrees over NCCL send/recv), re-homing every 8 steps" if let_stats and let_stats["let_evaluations"] > 0 else
+                           f"replicated tree, {n_gpus} Morton slices of targets, NCCL all-gather of positions"),
                        "l2": "no flush: per-step working set (~210 B/body state+sort+tree) exceeds the 126 MB L2 and is rewritten every build"},
             "interactions_per_step": inter / args.steps, "opened_per_step": opened / args.steps,
             "phases_ms_per_evaluation": {"build": build_ms, "walk": walk_ms},
             "roofline": roofline, "roofline_build": roofline_build, "cpu_baseline": cpu, "e2e": e2e, "configs0": c1, "reuse_acc_mode": reuse,
             "gpu_launches": launches, "clocks": clocks,
         }
+        if let_stats:
+            line["domain_mode_rank0"] = let_stats
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -48,6 +48,13 @@ extern "C" {
                                   * unchanged positions (BarnesHutAlg.kt:407-408 recomputes them).
                                   * Result-identical; automatically suspended after anything that
                                   * changes the inputs (set_bodies, Config, merge, jitter).       */
+#define BH_FLAG_LET          4u  /* CUDA engine, multi-GPU (bh_comm_init): DOMAIN mode.  Every rank
+                                  * builds only the tree of its own Morton range and walks its bodies
+                                  * over a locally essential tree (top tree from all-reduced level
+                                  * summaries + imported boundary subtrees) instead of replicating the
+                                  * whole tree; no per-step all-gather of positions.  Bit-identical to
+                                  * a single-GPU run; falls back to the replicated tree while the merge
+                                  * rule is enabled.  Env BH_LET=0/1 overrides.                      */
 
 typedef struct bh_engine bh_engine;
 
@@ -241,6 +248,10 @@ int bh_get_tree(bh_engine* e, int64_t cap, int64_t* n_cells,
 int bh_build_tree(bh_engine* e);
 int bh_get_counters(bh_engine* e, bh_counters* out);
 int bh_reset_counters(bh_engine* e);
+/* domain-mode statistics (BH_FLAG_LET): out[0..9] = enabled, partition valid, level of the cut,
+ * LET evaluations, fallbacks to a re-homing build, cells of this rank's LET, cells imported,
+ * cells sent, own strays, items of the top tree (last evaluation). */
+int bh_get_let_stats(bh_engine* e, int64_t* out, int32_t n_out);
 /* per-body counts of the last evaluation (needs BH_FLAG_BODY_COUNTS) */
 int bh_get_body_counts(bh_engine* e, int32_t* interactions, int32_t* opened);
 

@@ -735,6 +735,12 @@ int bh_get_body_counts(bh_engine* e, int32_t* interactions, int32_t* opened) {
     return BH_OK;
 }
 
+int bh_get_let_stats(bh_engine* e, int64_t* out, int32_t n_out) {   // the port has no domain mode: all zero
+    if (!e || !out || n_out < 1) return BH_E_ARG;
+    for (int k = 0; k < n_out; ++k) out[k] = 0;
+    return BH_OK;
+}
+
 int bh_comm_unique_id(void*, int32_t) { return BH_E_UNSUPPORTED; }
 int bh_comm_init(bh_engine* e, int32_t, int32_t, const void*, int32_t) { return fail(e, BH_E_UNSUPPORTED, "bh_comm_init: the reference port has no NCCL transport"); }
 int bh_comm_init_external(bh_engine* e, int32_t rank, int32_t world) {

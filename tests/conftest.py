@@ -38,7 +38,8 @@ def _build_oracle():
 
 
 def _build_emul():
-    srcs = [os.path.join(ROOT, "tests", "emul", "bh_emul.cpp"), os.path.join(CSRC, "bh_core.h"), os.path.join(CSRC, "bh_export.h")]
+    srcs = [os.path.join(ROOT, "tests", "emul", "bh_emul.cpp"), os.path.join(CSRC, "bh_core.h"), os.path.join(CSRC, "bh_export.h"),
+            os.path.join(CSRC, "bh_let_core.h")]
     if not _newer(EMUL_SO, srcs):
         subprocess.check_call(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-fno-strict-aliasing", "-fPIC", "-shared", "-o", EMUL_SO,
                                os.path.join(ROOT, "tests", "emul", "bh_emul.cpp")])

@@ -30,8 +30,9 @@ def main():
     dist.init_process_group(backend, rank=rank, world_size=world)
     lib = bh_b200.load_cuda_library() if cuda else bh_b200.bind(os.path.join(ROOT, "oracle", "libbh_ref.so"))
     z = np.load(scene_path)
+    flags = int(os.environ.get("BH_TEST_FLAGS", "0"))
     e = bh_b200.NativeEngine(lib=lib, device=(rank % torch.cuda.device_count()) if cuda else 0, threads=2,
-                             rehome_interval=3)
+                             rehome_interval=int(os.environ.get("BH_TEST_REHOME", "3")), flags=flags)
     e.set_window(int(z["W"]), int(z["H"]))
     e.set_params(theta=float(z["theta"]), merge_min_dist=8.0 if merge else 0.0)
     if transport == "nccl":
@@ -42,8 +43,11 @@ def main():
     else:
         HostStagedStepper(e, dist, rank, world).step(steps)
     x, y, vx, vy, m = e.get_bodies()
+    ls = e.let_stats()
     np.savez(f"{out_prefix}.{rank}.npz", x=x, y=y, vx=vx, vy=vy, m=m, origin=e.get_origin(),
-             merged=e.counters()["total_merged"], interactions=e.counters()["total_interactions"])
+             merged=e.counters()["total_merged"], interactions=e.counters()["total_interactions"],
+             opened=e.counters()["total_opened"], let=np.array([ls[k] for k in sorted(ls)], np.int64),
+             let_keys=np.array(sorted(ls)))
     dist.barrier()
     dist.destroy_process_group()
 

@@ -26,12 +26,13 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _run_world(world, which, transport, scene_path, out_prefix, steps, merge, timeout=600):
+def _run_world(world, which, transport, scene_path, out_prefix, steps, merge, timeout=600, extra_env=None):
     port = _free_port()
     procs = []
     for r in range(world):
         env = dict(os.environ, RANK=str(r), WORLD_SIZE=str(world), LOCAL_RANK=str(r), MASTER_ADDR="127.0.0.1",
                    MASTER_PORT=str(port), OMP_NUM_THREADS="1")
+        env.update(extra_env or {})
         procs.append(subprocess.Popen([sys.executable, WORKER, which, transport, scene_path, out_prefix, str(steps), str(merge)],
                                       env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
     outs = []
@@ -122,3 +123,38 @@ def test_cuda_nccl_is_bit_identical_to_one_gpu(cuda_lib, tmp_path, merge):
     ranks = _run_world(world, "cuda", "nccl", path, str(tmp_path / "out"), 7, merge)
     single, origin, ctr = _single(cuda_lib, scene, 7, merge)
     _assert_identical(ranks, single, origin, ctr)
+
+
+LET_CASES = [
+    ("two-disk 40k", lambda: scenes.snap_f32(scenes.default_two_disks(n1=32000, n2=8000, seed=31)), 0.5, 9, 3),
+    ("cloud 100k θ0.8", lambda: scenes.snap_f32(scenes.make_uniform_random(100_000, 0.5, seed=32)), 0.8, 6, 2),
+    ("two-disk 2k (coarsest cut)", lambda: scenes.snap_f32(scenes.default_two_disks(n1=1500, n2=500, seed=22)), 0.3, 7, 3),
+]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,gen,theta,steps,rehome", LET_CASES, ids=[c[0] for c in LET_CASES])
+def test_cuda_domain_mode_is_bit_identical_to_one_gpu(cuda_lib, tmp_path, name, gen, theta, steps, rehome):
+    """BH_FLAG_LET: every rank builds only its own Morton range and walks a locally essential tree
+    (no replicated tree, no per-step all-gather of positions).  State after several steps — re-homing
+    builds, LET evaluations with strays in between — bit-identical to one GPU; interaction and
+    opened-cell totals equal."""
+    import torch
+    world = min(torch.cuda.device_count(), 4)
+    if world < 2:
+        pytest.skip("needs >= 2 GPUs (run with gpurun --gpus 2)")
+    scene = gen()
+    path = str(tmp_path / "scene.npz")
+    np.savez(path, x=scene[0], y=scene[1], vx=scene[2], vy=scene[3], m=scene[4], W=2400, H=800, theta=theta)
+    ranks = _run_world(world, "cuda", "nccl", path, str(tmp_path / "out"), steps, 0,
+                       extra_env={"BH_TEST_FLAGS": str(bh_b200.BH_FLAG_LET), "BH_TEST_REHOME": str(rehome)})
+    e = make_engine(cuda_lib, scene, theta=theta, merge_min_dist=0.0)
+    e.step(steps)
+    single, ctr = e.get_bodies(), e.counters()
+    for z in ranks:
+        for k, nm in enumerate(("x", "y", "vx", "vy", "m")):
+            assert (z[nm] == single[k]).all(), nm
+        st = dict(zip([str(s) for s in z["let_keys"]], [int(v) for v in z["let"]]))
+        assert st["enabled"] == 1 and st["let_evaluations"] > 0 and st["fallbacks"] == 0, st
+    assert sum(int(z["interactions"]) for z in ranks) == ctr["total_interactions"]
+    assert sum(int(z["opened"]) for z in ranks) == ctr["total_opened"]

@@ -1,0 +1,85 @@
+"""Locally essential trees (csrc/bh_let_core.h), emulated for P ranks on the CPU: every rank builds the
+tree of its own Morton code range, the level summaries are merged, and each rank assembles its LET (top
+tree + own blocks + imported blocks + far roots).  A body's walk over its rank's LET must visit the
+same cells in the same order as its walk over the global tree: accelerations BIT-IDENTICAL, opened
+counts equal, interaction counts equal (a stray additionally meets its own leaf, which the CUDA engine
+resolves by looking the leaf up in the imported block)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from bh_b200 import scenes
+
+D = C.POINTER(C.c_double)
+I32 = C.POINTER(C.c_int32)
+I64 = C.POINTER(C.c_int64)
+
+
+def _dp(a):
+    return a.ctypes.data_as(D) if a is not None else None
+
+
+def _global(emul, scene, W, H, theta):
+    x, y, vx, vy, m = (np.ascontiguousarray(a, np.float64) for a in scene)
+    n = len(x)
+    ax, ay, ci, co, st = np.empty(n), np.empty(n), np.empty(n, np.int32), np.empty(n, np.int32), np.zeros(8, np.int64)
+    emul.bh_emul_accelerations(n, _dp(x), _dp(y), _dp(m), C.c_double(W / 2), C.c_double(H / 2), C.c_double(max(W, H) / 2 + 2),
+                               C.c_double(theta), C.c_double(1.0), C.c_double(80.0), _dp(ax), _dp(ay), ci.ctypes.data_as(I32),
+                               co.ctypes.data_as(I32), None, None, None, st.ctypes.data_as(I64))
+    return ax, ay, ci, co, st
+
+
+def _let(emul, scene, W, H, theta, P, ell, x0=None, y0=None):
+    x, y, vx, vy, m = (np.ascontiguousarray(a, np.float64) for a in scene)
+    n = len(x)
+    ax, ay, ci, co, st = np.empty(n), np.empty(n), np.empty(n, np.int32), np.empty(n, np.int32), np.zeros(8, np.int64)
+    rc = emul.bh_emul_let(n, _dp(x0), _dp(y0), _dp(x), _dp(y), _dp(m), C.c_double(W / 2), C.c_double(H / 2),
+                          C.c_double(max(W, H) / 2 + 2), C.c_double(theta), C.c_double(1.0), C.c_double(80.0), P, ell, _dp(ax), _dp(ay),
+                          ci.ctypes.data_as(I32), co.ctypes.data_as(I32), st.ctypes.data_as(I64))
+    assert rc == 0
+    return ax, ay, ci, co, st
+
+
+def _oob_scene():
+    s = scenes.make_uniform_random(3000, 0.5, seed=5)
+    s[0][:50] += 3000.0
+    s[4][100:120] = 0.0
+    return s
+
+
+CASES = [
+    ("two-disk P2", lambda: scenes.snap_f32(scenes.default_two_disks()), 0.5, 2, 3, 0.0),
+    ("two-disk P8", lambda: scenes.snap_f32(scenes.default_two_disks()), 0.5, 8, 5, 0.0),
+    ("two-disk θ0.3 P3", lambda: scenes.snap_f32(scenes.default_two_disks(seed=11)), 0.3, 3, 4, 0.0),
+    ("two-disk drifted (strays)", lambda: scenes.snap_f32(scenes.default_two_disks()), 0.5, 4, 4, 0.5),
+    ("cloud θ1.6 P8", lambda: scenes.make_uniform_random(20000, 0.5), 1.6, 8, 5, 0.0),
+    ("cloud θ0.2 drifted P4", lambda: scenes.make_uniform_random(20000, 0.5, seed=4), 0.2, 4, 3, 2.0),
+    ("out-of-box + zero mass", _oob_scene, 1.0, 4, 3, 0.0),
+    ("n=2", lambda: scenes.make_uniform_random(2, 0.5), 0.5, 2, 2, 0.0),
+    ("n=1", lambda: scenes.make_uniform_random(1, 0.5), 0.5, 2, 2, 0.0),
+    ("theta=0", lambda: scenes.make_uniform_random(300, 0.5, seed=8), 0.0, 4, 2, 0.0),
+    ("auto level", lambda: scenes.make_uniform_random(60000, 0.5, seed=9), 0.5, 8, 0, 0.0),
+]
+
+
+@pytest.mark.parametrize("name,gen,theta,P,ell,drift", CASES, ids=[c[0] for c in CASES])
+def test_let_walk_is_bit_identical_to_the_global_tree(emul_lib, name, gen, theta, P, ell, drift):
+    scene = gen()
+    W, H = 2400, 800
+    x0 = y0 = None
+    if drift > 0:   # home ranks and code ranges from the old positions, trees from the drifted ones
+        rng = np.random.default_rng(5)
+        x0, y0 = np.ascontiguousarray(scene[0]), np.ascontiguousarray(scene[1])
+        scene = (scene[0] + rng.normal(0, drift, len(x0)), scene[1] + rng.normal(0, drift, len(x0))) + tuple(scene[2:])
+    g = _global(emul_lib, scene, W, H, theta)
+    l = _let(emul_lib, scene, W, H, theta, P, ell, x0, y0)
+    assert np.array_equal(g[0], l[0], equal_nan=True) and np.array_equal(g[1], l[1], equal_nan=True)
+    assert (g[3] == l[3]).all()                                   # opened cells per body
+    d = l[2] - g[2]
+    assert ((d == 0) | (d == 1)).all() and np.count_nonzero(d) <= l[4][2]   # +1 only for strays (own leaf not resolved here)
+    if drift > 0:
+        assert l[4][2] > 0
+    assert l[4][3] == 0                                           # no guest inside a jitter cluster
+    if theta >= 0.5 and ell == 0:
+        assert l[4][4] < g[4][1]                                  # a rank's LET is smaller than the global tree

@@ -202,7 +202,8 @@ def test_tree_potential_converges_to_the_pair_sum(oracle_lib):
     assert abs(t0["potential"] - d["potential"]) <= 1e-12 * abs(d["potential"])
     assert abs(t5["potential"] - d["potential"]) <= 5e-3 * abs(d["potential"])      # monopole-only cells
     assert t5["kinetic"] == d["kinetic"] and t5["px"] == d["px"] and t5["py"] == d["py"]
-    assert e.energy_tree()["potential"] == t5["potential"]          # theta <= 0: the engine's theta
+    # theta <= 0: the engine's theta (the port sums per-thread partial potentials, whose split varies between calls)
+    assert abs(e.energy_tree()["potential"] - t5["potential"]) <= 1e-13 * abs(t5["potential"])
 
 
 def test_jvm_roundtrip_format(tmp_path, oracle_lib):
