@@ -20,6 +20,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <new>
 #include <string>
@@ -168,6 +169,7 @@ struct bh_engine {
     bool let_ready() const;
     int sync_positions();
     int let_partition();
+    int let_map_peers();
     int let_evaluate(int slot);
     int evaluate_slice(int slot);
 
@@ -232,6 +234,7 @@ struct bh_engine {
         if (mm <= cell_cap) return BH_OK;
         if (mm >= (int64_t)1 << 31) return fail(BH_E_ARG, "tree has more than 2^31 cells");
         const int64_t c = std::max<int64_t>(mm + mm / 8, 2048);
+        let.part_valid = false;      // peers map these arrays (let_map_peers): re-partition and re-map at the next re-homing
         free_cells();
         BH_TRY(dev_alloc(&cell, c)); BH_TRY(dev_alloc(&cd, c)); BH_TRY(dev_alloc(&sk, c));
         BH_TRY(dev_alloc(&arrived, c));
@@ -553,6 +556,7 @@ struct bh_engine {
         BH_RC(evaluate_slice(4));
         my_slice(&lo, &hi);
         BH_RC(kick(lo, hi, dtHalf, dt, 0));
+        if (world > 1) vel_valid = false;   // (a domain-mode fallback may have re-homed, i.e. replicated the velocities, inside this evaluation)
         acc_valid = !jitter_active;      // a jittering build mutated positions: the next build will again
         acc_par = par;
         phase = 2;
@@ -1294,6 +1298,9 @@ int bh_reset_counters(bh_engine* e) {
     E_TRY(cudaMemsetAsync(e->tot, 0, sizeof(DevTotals), e->st));
     E_TRY(cudaStreamSynchronize(e->st));
     const bh_counters keep = e->ctr;
+    for (auto& v : e->let.ms_phase) v = 0.0;
+    for (auto& v : e->let.cpu_us) v = 0.0;
+    e->let.n_folds = 0; e->let.pe_armed = false;
     e->ctr = bh_counters{};
     e->ctr.n_in_tree = keep.n_in_tree; e->ctr.n_out_of_box = keep.n_out_of_box; e->ctr.n_cells = keep.n_cells;
     e->ctr.n_internal = keep.n_internal; e->ctr.key_levels = keep.key_levels; e->ctr.max_depth = keep.max_depth;
@@ -1349,6 +1356,7 @@ int bh_comm_init(bh_engine* e, int32_t rank, int32_t world, const void* id, int3
     // domain mode: BH_FLAG_LET, or BH_LET=1/0 in the environment (overrides the flag)
     e->let.enabled = (e->cfg.flags & BH_FLAG_LET) != 0;
     if (const char* s = getenv("BH_LET")) e->let.enabled = atoi(s) != 0;
+    if (const char* s = getenv("BH_LET_MIN_WORLD")) e->let.min_world = std::max(2, atoi(s));
     if (world > 16) e->let.enabled = false;
     if (e->let.enabled) e->rehome_due = true;
     return BH_OK;
@@ -1398,9 +1406,24 @@ int bh_import_slices(bh_engine* e, int32_t field, int64_t n, const double* a, co
 
 int bh_get_let_stats(bh_engine* e, int64_t* out, int32_t n_out) {
     if (!e || !out || n_out < 1) return BH_E_ARG;
-    const int64_t v[10] = {e->let.enabled ? 1 : 0, e->let.part_valid ? 1 : 0, e->let.ell, e->let.evaluations, e->let.fallbacks,
-                           e->let.M, e->let.last_imported, e->let.last_sent, e->let.last_strays, e->let.n_items};
-    for (int k = 0; k < n_out && k < 10; ++k) out[k] = v[k];
+    int64_t v[40] = {e->let.enabled ? 1 : 0, e->let.part_valid ? 1 : 0, e->let.ell, e->let.evaluations, e->let.fallbacks,
+                     e->let.M, e->let.last_imported, e->let.last_sent, e->let.last_strays, e->let.n_items};
+    for (int k = 0; k < 7; ++k) v[10 + k] = 0;
+    v[17] = e->let.n_folds;
+    if (e->let.ipc_ok) v[0] = 2;   // enabled, blocks imported over peer memory
+    for (int k = 0; k < 8; ++k) v[18 + k] = 0;
+    v[25] = g_let_grows;
+    if (getenv("BH_LET_TIMERS") && atoi(getenv("BH_LET_TIMERS")) != 0 && e->let.n_folds > 0) {   // per-rank phase times (diagnostics)
+        char line[1024];
+        int off = snprintf(line, sizeof(line), "[let rank %d] evals %lld grows %lld gpu_us/eval:", e->rank, (long long)e->let.n_folds, (long long)g_let_grows);
+        for (int k = 0; k < 12; ++k) off += snprintf(line + off, sizeof(line) - off, " %.0f", e->let.ms_phase[k] * 1000.0 / (double)e->let.n_folds);
+        off += snprintf(line + off, sizeof(line) - off, "  cpu_us/eval:");
+        for (int k = 0; k < 12; ++k) off += snprintf(line + off, sizeof(line) - off, " %.0f", e->let.cpu_us[k] / (double)e->let.n_folds);
+        off += snprintf(line + off, sizeof(line) - off, "  M %d imported %lld own %lld walk_ms %.3f\n", e->let.M, (long long)e->let.last_imported,
+                        (long long)(e->let.cut[e->rank + 1] - e->let.cut[e->rank]), e->ctr.ms_walk / std::max<double>(1.0, (double)e->ctr.total_evaluations));
+        fputs(line, stderr);
+    }
+    for (int k = 0; k < n_out && k < 26; ++k) out[k] = v[k];
     return BH_OK;
 }
 

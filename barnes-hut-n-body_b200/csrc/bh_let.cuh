@@ -75,10 +75,14 @@ k_let_local(int n_own, const double* __restrict__ x, const double* __restrict__ 
         return;
     }
     const uint64_t key = grid.exact ? bh_morton_key_grid(grid, root.levels, px, py) : bh_morton_key(root, px, py);
+    // footprint: the lanes of a warp are Morton neighbours, so one lane per distinct coarse cell sets the bit
     const uint32_t q = bh_let_code(key, root.levels, lam);
     uint32_t* bits = reinterpret_cast<uint32_t*>(seg + LET_SEG_HDR);
-    const uint32_t bit = 1u << (q & 31u);
-    if (!(bits[q >> 5] & bit)) atomicOr(&bits[q >> 5], bit);
+    const unsigned same = __match_any_sync(__activemask(), q);
+    if ((threadIdx.x & 31) == (unsigned)(__ffs(same) - 1)) {
+        const uint32_t bit = 1u << (q & 31u);
+        if (!(__ldcg(&bits[q >> 5]) & bit)) atomicOr(&bits[q >> 5], bit);
+    }
     const uint32_t c = bh_let_code(key, root.levels, ell);
     if (c < c_lo || c >= c_hi) {
         const int k = atomicAdd(&dcnt[LET_D_STRAYS], 1);
@@ -132,7 +136,13 @@ __global__ void k_let_summary(BhTreeView t, int levels, int ell, const double* _
     bh_let_summary_body(t, levels, ell, i, lx[b], ly[b], (jflag && (jflag[b] & 1)) ? 0.0 : lm[b], table);
 }
 
-__global__ void k_let_flag(BhLetEntry* __restrict__ e, const int* __restrict__ flag) { e->count = *flag ? 1.0 : 0.0; }
+// this rank's retry flag: a guest in a jitter cluster, or some rank had more strays than a segment holds
+__global__ void k_let_flag(BhLetEntry* __restrict__ e, const int* __restrict__ flag, const double* __restrict__ segs,
+                           int64_t seg_len, int world) {
+    bool retry = *flag != 0;
+    for (int q = 0; q < world; ++q) retry |= segs[(size_t)q * seg_len + 1] != 0.0;
+    e->count = retry ? 1.0 : 0.0;
+}
 
 struct LetSplit { uint32_t cs[17]; int world, me; };
 __device__ __forceinline__ int let_owner(const LetSplit& s, uint32_t c) {
@@ -198,13 +208,52 @@ k_let_item_cnt(const uint64_t* __restrict__ ikey, const int* __restrict__ n_item
     else { icnt[j] = 0; iw[j] = 0; }
 }
 
+// up to 3 independent exclusive scans in one launch: block b scans in[b][0..n[b]) into out[b][0..n[b]] (out[n] = total)
+struct LetScanJob { const int* in[3]; int* out[3]; int n[3]; };
+__global__ void __launch_bounds__(1024) k_let_scans(LetScanJob job) {
+    const int* __restrict__ in = job.in[blockIdx.x];
+    int* __restrict__ out = job.out[blockIdx.x];
+    const int n = job.n[blockIdx.x];
+    __shared__ int s_warp[32];
+    __shared__ int s_carry;
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    if (tid == 0) s_carry = 0;
+    __syncthreads();
+    constexpr int IPT = 16;
+    for (int base = 0; base < n; base += 1024 * IPT) {
+        int v[IPT], sum = 0;
+#pragma unroll
+        for (int k = 0; k < IPT; ++k) { const int i = base + tid * IPT + k; v[k] = i < n ? in[i] : 0; sum += v[k]; }
+        int inc = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+        if (lane == 31) s_warp[w] = inc;
+        __syncthreads();
+        if (w == 0) {
+            int x = s_warp[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += t; }
+            s_warp[lane] = x;     // inclusive over warps
+        }
+        __syncthreads();
+        const int carry = s_carry;
+        int run = carry + (w > 0 ? s_warp[w - 1] : 0) + inc - sum;
+#pragma unroll
+        for (int k = 0; k < IPT; ++k) { const int i = base + tid * IPT + k; if (i < n) out[i] = run; run += v[k]; }
+        __syncthreads();
+        if (tid == 1023) s_carry = carry + s_warp[31];
+        __syncthreads();
+    }
+    if (tid == 0) out[n] = s_carry;
+}
+
 // the few numbers the host needs: items, LET cells, receive offset of every owner, send offset of every peer
 __global__ void k_let_collect(const int* __restrict__ item_first, uint32_t ncodes, const int* __restrict__ iS,
                               const int* __restrict__ iW, const int* __restrict__ recvoff, const int* __restrict__ sendoff,
-                              LetSplit sp, int* __restrict__ out) {
+                              LetSplit sp, const int* __restrict__ dcnt, int* __restrict__ out) {
     const int t = threadIdx.x;
     const int n = item_first[ncodes];
-    if (t == 0) { out[0] = n; out[1] = iS[n] + iW[n]; }
+    if (t == 0) { out[0] = n; out[1] = iS[n] + iW[n]; out[38] = dcnt[LET_D_STRAYS]; out[39] = dcnt[LET_D_GUESTS]; }
     const uint32_t mylen = sp.cs[sp.me + 1] - sp.cs[sp.me];
     if (t <= sp.world) {
         out[2 + t] = recvoff[sp.cs[t]];
@@ -229,20 +278,30 @@ k_let_pack(const BhLetEntry* __restrict__ table, LetSplit sp, const int* __restr
 }
 
 __global__ void __launch_bounds__(256)
-k_let_emit(BhLetItems it, BhCellS* __restrict__ sk, int levels, int ell, int* __restrict__ ilp, int* __restrict__ dst) {
+k_let_emit(BhLetItems it, BhCellS* __restrict__ sk, int* __restrict__ arrived, int levels, int ell, int* __restrict__ ilp,
+           int* __restrict__ dst) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= it.n) return;
     const int lp = bh_let_emit_item(it, sk, levels, j);
     ilp[j] = lp;
+    {   // arrive counters of the internal cells this item owns (the column in front of its leaf region)
+        const int first = it.S[j] + it.W[j];
+        for (int p = first; p < lp; ++p) arrived[p] = 0;
+    }
     const int type = it.type[j];
     if (type != BH_LET_TWIN1) dst[bh_let_code(it.key[j], levels, ell)] = (type == BH_LET_SINGLE) ? lp : lp - 1;
 }
 
-// one warp per code: own blocks from the local arrays, imported blocks from the receive buffer
+// the local-tree arrays of every rank, mapped into this process (CUDA IPC over NVLink peer memory)
+struct LetPeers { const BhCellD* cd[16]; const BhCellS* sk[16]; };
+
+// one warp per code: own blocks from the local arrays; imported blocks straight from the OWNER's local
+// arrays over NVLink peer memory (peers != nullptr), else from the receive buffer of the NCCL exchange
 __global__ void __launch_bounds__(256)
 k_let_blocks(BhTreeView let, const BhLetEntry* __restrict__ table, uint32_t ncodes, LetSplit sp, const int* __restrict__ nit,
              const int* __restrict__ blk, const int* __restrict__ dst, const int* __restrict__ recvoff,
-             const BhLetWire* __restrict__ recvbuf, const BhCellD* __restrict__ cd, const BhCellS* __restrict__ sk, double half) {
+             const BhLetWire* __restrict__ recvbuf, const BhCellD* __restrict__ cd, const BhCellS* __restrict__ sk, double half,
+             LetPeers peers, int use_peers) {
     const int64_t wid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (wid >= ncodes) return;
@@ -253,6 +312,12 @@ k_let_blocks(BhTreeView let, const BhLetEntry* __restrict__ table, uint32_t ncod
     if (c >= sp.cs[sp.me] && c < sp.cs[sp.me + 1]) {
         const int rp = (int)table[c].pos;
         for (int j = 1 + lane; j < B; j += 32) bh_let_place(let, bh_let_wire(cd, sk, rp + j, rp), d, j, half);
+    } else if (use_peers) {
+        const int o = let_owner(sp, c);
+        const BhCellD* __restrict__ pcd = peers.cd[o];
+        const BhCellS* __restrict__ psk = peers.sk[o];
+        const int rp = (int)table[c].pos;
+        for (int j = 1 + lane; j < B; j += 32) bh_let_place(let, bh_let_wire(pcd, psk, rp + j, rp), d, j, half);
     } else {
         const BhLetWire* in = recvbuf + recvoff[c];
         for (int j = 1 + lane; j < B; j += 32) bh_let_place(let, in[j - 1], d, j, half);
@@ -276,23 +341,35 @@ k_let_leafpos(int n_own, const int* __restrict__ lleaf, const double* __restrict
               BhRoot root, BhGrid grid, int ell, const BhLetEntry* __restrict__ table, const int* __restrict__ dst,
               const int* __restrict__ blk, BhTreeView let, int* __restrict__ leafpos) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= n_own) return;
-    const int p = lleaf[j];
-    const double px = lx[j], py = ly[j];
-    int out = -1;
-    if (p >= 0 || bh_root_contains(root, px, py)) {
+    const int lane = threadIdx.x & 31;
+    const bool live = j < n_own;
+    const int p = live ? lleaf[j] : -1;
+    const double px = live ? lx[j] : 0.0, py = live ? ly[j] : 0.0;
+    int out = -1, d = -1, B = 0;
+    bool search = false;
+    if (live && (p >= 0 || bh_root_contains(root, px, py))) {
         const uint64_t key = grid.exact ? bh_morton_key_grid(grid, root.levels, px, py) : bh_morton_key(root, px, py);
         const uint32_t c = bh_let_code(key, root.levels, ell);
-        const int d = dst[c];
+        d = dst[c];
         if (p >= 0) out = d + (p - (int)table[c].pos);
         else if (table[c].count == 1.0) out = d;                 // the stray is the only body of its code
-        else {
-            const int B = blk[c];
-            for (int q = d + 1; q < d + B; ++q)
-                if (let.sk[q].skip == q + 1 && let.cd[q].comx == px && let.cd[q].comy == py) { out = q; break; }
-        }
+        else { B = blk[c]; search = B > 1; }
     }
-    leafpos[j] = out;
+    // strays (rare): the whole warp scans the imported block for the leaf with the stray's exact coordinates
+    unsigned todo = __ballot_sync(0xffffffffu, search);
+    while (todo) {
+        const int src = __ffs(todo) - 1;
+        todo &= todo - 1;
+        const int sd = __shfl_sync(0xffffffffu, d, src), sB = __shfl_sync(0xffffffffu, B, src);
+        const double sx = __shfl_sync(0xffffffffu, px, src), sy = __shfl_sync(0xffffffffu, py, src);
+        int found = 0x7fffffff;
+        for (int q = sd + 1 + lane; q < sd + sB; q += 32)
+            if (let.sk[q].skip == q + 1 && let.cd[q].comx == sx && let.cd[q].comy == sy) { found = q; break; }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) found = min(found, __shfl_xor_sync(0xffffffffu, found, o));
+        if (lane == src && found != 0x7fffffff) out = found;
+    }
+    if (live) leafpos[j] = out;
 }
 
 // slices of the freshly re-homed (globally sorted) state, cut at code boundaries
@@ -316,12 +393,14 @@ __global__ void k_let_cut(const uint64_t* __restrict__ keys, int n_in, int n, in
     out[17 + r] = (int)cs;
 }
 
+int64_t g_let_grows = 0;
 template <class T>
 cudaError_t let_grow(T*& p, int64_t& cap, int64_t need) {
     if (need <= cap) return cudaSuccess;
+    ++g_let_grows;
     if (p) cudaFree(p);
     p = nullptr;
-    cap = need + need / 8 + 64;
+    cap = need + need / 2 + 64;      // generous: cudaFree + cudaMalloc stall the stream (more so with peer mappings)
     return cudaMalloc((void**)&p, (size_t)cap * sizeof(T));
 }
 
@@ -329,6 +408,8 @@ cudaError_t let_grow(T*& p, int64_t& cap, int64_t need) {
 
 struct bh_let_state {
     bool enabled = false;        // BH_FLAG_LET / BH_LET=1
+    int min_world = 4;           // smallest world the domain mode is used for (BH_LET_MIN_WORLD): below it the replicated
+                                 // build of the few-times-larger tree is cheaper than the fixed cost of assembling a LET
     bool part_valid = false;     // slices are cut at code boundaries (set by the re-homing build)
     bool pos_valid = true;       // positions of ALL bodies are current on this rank
     int ell = 0, lam = 0, bw = 0;
@@ -362,9 +443,26 @@ struct bh_let_state {
     double* hhdr = nullptr;       // pinned: world x 2 doubles
     int* hcut = nullptr;          // pinned: 2*17 ints
     int M = 0, n_items = 0;
+    // peer memory (CUDA IPC): every rank's local-tree arrays (cd, sk) mapped here
+    struct IpcPair { cudaIpcMemHandle_t cd, sk; };
+    bool ipc_wanted = true, ipc_ok = false;
+    IpcPair ipc_cached[16] = {};
+    bool ipc_open[16] = {false};
+    void* ipc_ptr_cd[16] = {nullptr};
+    void* ipc_ptr_sk[16] = {nullptr};
+    IpcPair* ipc_host = nullptr;      // pinned, world entries
+    double* ipc_dev = nullptr;        // world x sizeof(IpcPair) bytes (+ 1 double for the agreement flag)
+    LetPeers peers{};
     // statistics of the last LET evaluation
     int64_t last_imported = 0, last_sent = 0, last_strays = 0, last_guests_max = 0, evaluations = 0, fallbacks = 0;
-    double ms_exchange = 0.0;
+    // phase timers of let_evaluate (CUDA events, folded at the start of the next evaluation)
+    static constexpr int NPH = 14;
+    cudaEvent_t pe[NPH + 1] = {};
+    bool pe_armed = false;
+    int64_t n_folds = 0;
+    double ms_phase[NPH] = {0};
+    double cpu_us[NPH] = {0};      // host time between the same points
+    double cpu_t[NPH + 1] = {0};
 
     void release() {
         void* ptrs[] = {lx, ly, lm, lperm, lleaf, segs, table, nit, blk, recvsz, recvoff, item_first, dst, sendsz, sendoff, ikey,
@@ -373,6 +471,10 @@ struct bh_let_state {
         if (hcollect) cudaFreeHost(hcollect);
         if (hhdr) cudaFreeHost(hhdr);
         if (hcut) cudaFreeHost(hcut);
+        for (int q = 0; q < 16; ++q) if (ipc_open[q]) { cudaIpcCloseMemHandle(ipc_ptr_cd[q]); cudaIpcCloseMemHandle(ipc_ptr_sk[q]); }
+        if (ipc_host) cudaFreeHost(ipc_host);
+        if (ipc_dev) cudaFree(ipc_dev);
+        for (auto& e : pe) if (e) cudaEventDestroy(e);
     }
 };
 

@@ -5,7 +5,7 @@
 #define LET_GROW(field, need) BH_TRY(let_grow(let.field, let.field##_cap, (int64_t)(need)))
 
 inline bool bh_engine::let_usable() const {
-    return let.enabled && world > 1 && world <= 16 && transport == T_NCCL && !merge_enabled();
+    return let.enabled && world >= let.min_world && world <= 16 && transport == T_NCCL && !merge_enabled();
 }
 inline bool bh_engine::let_ready() const {
     return let_usable() && let.part_valid && let.n_part == n && !rehome_due && let.part_root.cx == par.root_cx &&
@@ -47,12 +47,78 @@ inline int bh_engine::let_partition() {
     let.split.world = world; let.split.me = rank;
     for (int r = 0; r <= world; ++r) { let.cut[r] = let.hcut[r]; let.split.cs[r] = (uint32_t)let.hcut[17 + r]; }
     for (int r = 0; r < world; ++r) if (let.cut[r + 1] < let.cut[r]) return BH_OK;
-    let.stray_cap = std::max<int64_t>(1024, n / world / 16);
+    // stray slots per rank: the local build (own slice + (P-1) x stray_cap guest slots) runs in the engine's per-body buffers
+    int64_t max_slice = 0;
+    for (int r = 0; r < world; ++r) max_slice = std::max(max_slice, let.cut[r + 1] - let.cut[r]);
+    const int64_t room = (cap - max_slice) / (world - 1);
+    let.stray_cap = std::max<int64_t>(n / world / 128, std::min<int64_t>(1024, room));
+    if (let.stray_cap < 16 || let.stray_cap > room) return BH_OK;
+    if (const char* sc_env = getenv("BH_LET_STRAY_CAP")) let.stray_cap = std::max(1, atoi(sc_env));   // test hook: force overflows -> fallbacks
     let.seg_len = LET_SEG_HDR + let.bw + 4 * let.stray_cap;
+    BH_RC(let_map_peers());
     let.part_root = root;
     let.n_part = n;
     let.part_valid = true;
     let.n_declined = -1;
+    return BH_OK;
+}
+
+// Map every rank's local-tree arrays (cd, sk) into this process (CUDA IPC; NVLink peer memory), so that
+// k_let_blocks reads the blocks it imports straight from their owner — no packing, no send/recv.  The
+// arrays are the engine's own cell arrays: sized by the re-homing build of the GLOBAL tree, so a local
+// tree always fits and the pointers only change when a re-homing build grows them, i.e. right before
+// this (collective) call.  The existing collectives order the accesses: importers read after the table
+// all-reduce (issued behind the owner's climb) and an owner overwrites its arrays only behind the next
+// segment all-gather / position gather, which cannot complete before every rank has got there.
+// All ranks agree (all-reduce) on whether the mapping worked; if not, blocks go through ncclSend/ncclRecv.
+inline int bh_engine::let_map_peers() {
+    bhcomm::Api& A = bhcomm::api();
+    typedef bh_let_state::IpcPair IpcPair;
+    static_assert(sizeof(IpcPair) % sizeof(double) == 0, "IpcPair must be a whole number of doubles");
+    const size_t pair_d = sizeof(IpcPair) / sizeof(double);
+    if (const char* s = getenv("BH_LET_IPC")) let.ipc_wanted = atoi(s) != 0;
+    if (!let.ipc_host) {
+        BH_TRY(cudaMallocHost((void**)&let.ipc_host, 17 * sizeof(IpcPair)));
+        BH_TRY(cudaMalloc((void**)&let.ipc_dev, 17 * sizeof(IpcPair) + 64));
+    }
+    double failed = 0.0;
+    IpcPair mine;
+    memset(&mine, 0, sizeof(mine));
+    if (!let.ipc_wanted || cudaIpcGetMemHandle(&mine.cd, cd) != cudaSuccess || cudaIpcGetMemHandle(&mine.sk, sk) != cudaSuccess) failed = 1.0;
+    (void)cudaGetLastError();
+    let.ipc_host[rank] = mine;
+    BH_TRY(cudaMemcpyAsync(reinterpret_cast<char*>(let.ipc_dev) + (size_t)rank * sizeof(IpcPair), &let.ipc_host[rank], sizeof(IpcPair),
+                           cudaMemcpyHostToDevice, st));
+    int rc = A.AllGather(reinterpret_cast<char*>(let.ipc_dev) + (size_t)rank * sizeof(IpcPair), let.ipc_dev, pair_d, bhcomm::kFloat64, comm, st);
+    if (rc != bhcomm::kSuccess) return nccl_fail(rc, "ncclAllGather(ipc handles)");
+    BH_TRY(cudaMemcpyAsync(let.ipc_host, let.ipc_dev, (size_t)world * sizeof(IpcPair), cudaMemcpyDeviceToHost, st));
+    BH_TRY(cudaStreamSynchronize(st));
+    if (failed == 0.0) {
+        for (int q = 0; q < world && failed == 0.0; ++q) {
+            if (q == rank) { let.peers.cd[q] = cd; let.peers.sk[q] = sk; continue; }
+            if (let.ipc_open[q] && memcmp(&let.ipc_cached[q], &let.ipc_host[q], sizeof(IpcPair)) == 0) continue;
+            if (let.ipc_open[q]) { cudaIpcCloseMemHandle(let.ipc_ptr_cd[q]); cudaIpcCloseMemHandle(let.ipc_ptr_sk[q]); let.ipc_open[q] = false; }
+            void *pc = nullptr, *ps = nullptr;
+            if (cudaIpcOpenMemHandle(&pc, let.ipc_host[q].cd, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { failed = 1.0; break; }
+            if (cudaIpcOpenMemHandle(&ps, let.ipc_host[q].sk, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+                cudaIpcCloseMemHandle(pc); failed = 1.0; break;
+            }
+            let.ipc_ptr_cd[q] = pc; let.ipc_ptr_sk[q] = ps; let.ipc_open[q] = true;
+            let.ipc_cached[q] = let.ipc_host[q];
+            let.peers.cd[q] = static_cast<const BhCellD*>(pc);
+            let.peers.sk[q] = static_cast<const BhCellS*>(ps);
+        }
+        (void)cudaGetLastError();
+    }
+    // agreement: peer memory is used only if it works on every rank
+    double* flag = let.ipc_dev + 17 * pair_d;
+    BH_TRY(cudaMemcpyAsync(flag, &failed, sizeof(double), cudaMemcpyHostToDevice, st));
+    rc = A.AllReduce(flag, flag, 1, bhcomm::kFloat64, bhcomm::kSum, comm, st);
+    if (rc != bhcomm::kSuccess) return nccl_fail(rc, "ncclAllReduce(ipc agreement)");
+    double total = 1.0;
+    BH_TRY(cudaMemcpyAsync(&total, flag, sizeof(double), cudaMemcpyDeviceToHost, st));
+    BH_TRY(cudaStreamSynchronize(st));
+    let.ipc_ok = total == 0.0;
     return BH_OK;
 }
 
@@ -69,6 +135,24 @@ inline int bh_engine::let_evaluate(int slot) {
     root = BhRoot{par.root_cx, par.root_cy, par.root_half, bh_key_levels(par.root_half)};
     const BhGrid grid = bh_make_grid(root);
     BH_TRY(cudaEventRecord(ev[slot + 0], st));
+    // phase timers: fold the previous evaluation's events (complete by now: that evaluation ended in a walk + sync)
+    static const bool timers = getenv("BH_LET_TIMERS") && atoi(getenv("BH_LET_TIMERS")) != 0;
+    if (!let.pe[0]) for (auto& e : let.pe) BH_TRY(cudaEventCreate(&e));
+    if (timers && let.pe_armed && cudaEventSynchronize(let.pe[bh_let_state::NPH]) == cudaSuccess) {
+        let.n_folds++;
+        for (int k = 0; k < bh_let_state::NPH; ++k) {
+            float ms = 0.f;
+            if (cudaEventElapsedTime(&ms, let.pe[k], let.pe[k + 1]) == cudaSuccess) let.ms_phase[k] += ms;
+        }
+    }
+    let.pe_armed = false;
+#define LET_PHASE(k)                                                                                   \
+    do {                                                                                                \
+        BH_TRY(cudaEventRecord(let.pe[k], st));                                                         \
+        let.cpu_t[k] = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count(); \
+        if ((k) > 0) let.cpu_us[(k) - 1] += let.cpu_t[k] - let.cpu_t[(k) - 1];                            \
+    } while (0)
+    LET_PHASE(0);
 
     // ---- 1. local arrays, footprint, strays
     const int64_t nl_max = (int64_t)n_own + (int64_t)(P - 1) * cap;
@@ -82,31 +166,21 @@ inline int bh_engine::let_evaluate(int slot) {
                                                             cap, let.lx, let.ly, let.lm, let.lperm, myseg, let.bw, let.dcnt);
     k_let_seg_header<<<1, 1, 0, st>>>(myseg, let.dcnt, cap);
     ctr.kernel_launches += 3;
+    LET_PHASE(1);   // 0: own slice -> local arrays, footprint, strays
     int rc = A.AllGather(myseg, let.segs, (size_t)let.seg_len, bhcomm::kFloat64, comm, st);
     if (rc != bhcomm::kSuccess) return nccl_fail(rc, "ncclAllGather(segments)");
-    BH_TRY(cudaMemcpy2DAsync(let.hhdr, 2 * sizeof(double), let.segs, (size_t)let.seg_len * sizeof(double), 2 * sizeof(double), (size_t)P,
-                             cudaMemcpyDeviceToHost, st));
-    BH_TRY(cudaStreamSynchronize(st));
-    int64_t others = 0, strays_all = 0;
-    bool overflow = false;
-    for (int q = 0; q < P; ++q) {
-        strays_all += (int64_t)let.hhdr[2 * q];
-        if (q != rank) others += (int64_t)let.hhdr[2 * q];
-        overflow |= let.hhdr[2 * q + 1] != 0.0;
-    }
-    if (overflow) return BH_LET_RETRY;
-    let.last_strays = (int64_t)let.hhdr[2 * rank];
-    // ---- 2. guests
+    LET_PHASE(2);   // 1: segment all-gather (includes waiting for the slowest rank)
+    // ---- 2. guests: at most (P-1)*cap; unused slots stay NaN = outside the root box = not in the tree
+    const int64_t others = (int64_t)(P - 1) * cap;
     const int n_loc = n_own + (int)others;
-    if (others > 0) {
-        BH_TRY(cudaMemsetAsync(let.lx + n_own, 0xFF, (size_t)others * sizeof(double), st));   // NaN: outside the root box
-        BH_TRY(cudaMemsetAsync(let.ly + n_own, 0xFF, (size_t)others * sizeof(double), st));
-        BH_TRY(cudaMemsetAsync(let.lm + n_own, 0, (size_t)others * sizeof(double), st));
-        BH_TRY(cudaMemsetAsync(let.lperm + n_own, 0, (size_t)others * sizeof(int), st));
-        k_let_guests<<<grid_for((int64_t)P * cap, 256), 256, 0, st>>>(let.segs, let.seg_len, let.bw, cap, P, rank, root, grid, ell, c_lo, c_hi,
-                                                                       n_own, (int)others, let.lx, let.ly, let.lm, let.lperm, let.dcnt);
-        ctr.kernel_launches += 1;
-    }
+    BH_TRY(cudaMemsetAsync(let.lx + n_own, 0xFF, (size_t)others * sizeof(double), st));
+    BH_TRY(cudaMemsetAsync(let.ly + n_own, 0xFF, (size_t)others * sizeof(double), st));
+    BH_TRY(cudaMemsetAsync(let.lm + n_own, 0, (size_t)others * sizeof(double), st));
+    BH_TRY(cudaMemsetAsync(let.lperm + n_own, 0, (size_t)others * sizeof(int), st));
+    k_let_guests<<<grid_for((int64_t)P * cap, 256), 256, 0, st>>>(let.segs, let.seg_len, let.bw, cap, P, rank, root, grid, ell, c_lo, c_hi,
+                                                                   n_own, (int)others, let.lx, let.ly, let.lm, let.lperm, let.dcnt);
+    ctr.kernel_launches += 1;
+    LET_PHASE(3);   // 2: guests
     // ---- 3. the single-GPU build on the local arrays (keys outside [c_lo, c_hi) -> not in the tree)
     {
         double *sx = x, *sy = y, *sm = m;
@@ -119,6 +193,7 @@ inline int bh_engine::let_evaluate(int slot) {
         x = sx; y = sy; m = sm; perm = sperm; leafpos = sleaf; n = sn;
         BH_RC(brc);
     }
+    LET_PHASE(4);   // 3: local build
     tree_valid = false;              // the engine's cell arrays hold the LOCAL tree: exports rebuild the global one
     const bool jit = jitter_active;
     if (jit && n_in > 0) {
@@ -132,9 +207,11 @@ inline int bh_engine::let_evaluate(int slot) {
         k_let_summary<<<grid_for(n_in, 256), 256, 0, st>>>(view(), root.levels, ell, let.lx, let.ly, let.lm, jit ? jflag : nullptr, let.table);
         ctr.kernel_launches += 1;
     }
-    k_let_flag<<<1, 1, 0, st>>>(let.table + ncodes + rank, let.dcnt + LET_D_FLAG);
+    k_let_flag<<<1, 1, 0, st>>>(let.table + ncodes + rank, let.dcnt + LET_D_FLAG, let.segs, let.seg_len, P);
+    LET_PHASE(5);   // 4: summaries
     rc = A.AllReduce(let.table, let.table, (size_t)(ncodes + P) * 6, bhcomm::kFloat64, bhcomm::kSum, comm, st);
     if (rc != bhcomm::kSuccess) return nccl_fail(rc, "ncclAllReduce(table)");
+    LET_PHASE(6);   // 5: table all-reduce
     // ---- 5. plan
     const int n_slots = 2 * (int)ncodes;
     LET_GROW(nit, ncodes + 1); LET_GROW(blk, ncodes + 1); LET_GROW(recvsz, ncodes + 1); LET_GROW(recvoff, ncodes + 2);
@@ -145,21 +222,42 @@ inline int bh_engine::let_evaluate(int slot) {
     const double theta2 = par.theta * par.theta;
     k_let_plan<<<grid_for(ncodes, 256), 256, 0, st>>>(let.table, ncodes, let.segs, let.seg_len, let.split, theta2, par.soft2, root, ell,
                                                         let.nit, let.blk, let.recvsz, let.sendsz);
-    BH_RC(excl_scan(let.nit, (int)ncodes, let.item_first));
-    BH_RC(excl_scan(let.recvsz, (int)ncodes, let.recvoff));
-    BH_RC(excl_scan(let.sendsz, (int)(P * mylen), let.sendoff));
+    // exclusive scans: one fused single-block launch while the arrays are small, the multi-block look-back scan beyond
+    const bool small_scans = n_slots <= 32768;
+    if (small_scans) {
+        LetScanJob job{};
+        job.in[0] = let.nit; job.out[0] = let.item_first; job.n[0] = (int)ncodes;
+        job.in[1] = let.recvsz; job.out[1] = let.recvoff; job.n[1] = (int)ncodes;
+        job.in[2] = let.sendsz; job.out[2] = let.sendoff; job.n[2] = let.ipc_ok ? 0 : (int)(P * mylen);
+        k_let_scans<<<3, 1024, 0, st>>>(job);
+    } else {
+        BH_RC(excl_scan(let.nit, (int)ncodes, let.item_first));
+        BH_RC(excl_scan(let.recvsz, (int)ncodes, let.recvoff));
+        if (!let.ipc_ok) BH_RC(excl_scan(let.sendsz, (int)(P * mylen), let.sendoff));
+    }
+    if (let.ipc_ok) BH_TRY(cudaMemsetAsync(let.sendoff, 0, ((size_t)P * mylen + 1) * sizeof(int), st));
     k_let_items<<<grid_for(ncodes, 256), 256, 0, st>>>(ncodes, let.item_first, let.blk, root.levels, ell, let.ikey, let.itype, let.iw);
     k_let_item_cnt<<<grid_for(n_slots, 256), 256, 0, st>>>(let.ikey, let.item_first + ncodes, n_slots, root.levels, let.icnt, let.iw);
-    BH_RC(excl_scan(let.icnt, n_slots, let.iS));
-    BH_RC(excl_scan(let.iw, n_slots, let.iW));
-    k_let_collect<<<1, 32, 0, st>>>(let.item_first, ncodes, let.iS, let.iW, let.recvoff, let.sendoff, let.split, let.dcollect);
+    if (small_scans) {
+        LetScanJob job{};
+        job.in[0] = let.icnt; job.out[0] = let.iS; job.n[0] = n_slots;
+        job.in[1] = let.iw; job.out[1] = let.iW; job.n[1] = n_slots;
+        k_let_scans<<<2, 1024, 0, st>>>(job);
+    } else {
+        BH_RC(excl_scan(let.icnt, n_slots, let.iS));
+        BH_RC(excl_scan(let.iw, n_slots, let.iW));
+    }
+    k_let_collect<<<1, 32, 0, st>>>(let.item_first, ncodes, let.iS, let.iW, let.recvoff, let.sendoff, let.split, let.dcnt, let.dcollect);
     ctr.kernel_launches += 5;
     BH_TRY(cudaMemcpyAsync(let.hcollect, let.dcollect, 40 * sizeof(int), cudaMemcpyDeviceToHost, st));
     BH_TRY(cudaMemcpy2DAsync(let.hhdr, sizeof(double), let.table + ncodes, sizeof(BhLetEntry), sizeof(double), (size_t)P,
                              cudaMemcpyDeviceToHost, st));
     BH_TRY(cudaStreamSynchronize(st));
     BH_TRY(cudaGetLastError());
-    for (int q = 0; q < P; ++q) if (let.hhdr[q] != 0.0) return BH_LET_RETRY;   // a stray sits in a jitter cluster of its host
+    LET_PHASE(7);   // 6: plan + scans + host sync
+    // a stray sits in a jitter cluster of its host, or a rank had more strays than its segment holds
+    for (int q = 0; q < P; ++q) if (let.hhdr[q] != 0.0) return BH_LET_RETRY;
+    let.last_strays = let.hcollect[38];
     let.n_items = let.hcollect[0];
     let.M = let.hcollect[1];
     const int* roff = let.hcollect + 2;
@@ -170,38 +268,46 @@ inline int bh_engine::let_evaluate(int slot) {
         let.pos_valid = false;
     }
     // ---- 6. blocks to the ranks that may open them
-    LET_GROW(sendbuf, (std::max(1, soff[P]))); LET_GROW(recvbuf, (std::max(1, roff[P])));
     LET_GROW(cell, (int64_t)let.M + 1); LET_GROW(cd, (int64_t)let.M + 1); LET_GROW(sk, (int64_t)let.M + 1); LET_GROW(arrived, (int64_t)let.M + 1);
-    if (soff[P] > 0) {
-        k_let_pack<<<grid_for((int64_t)P * mylen * 32, 256), 256, 0, st>>>(let.table, let.split, let.sendsz, let.sendoff, cd, sk, let.sendbuf);
-        ctr.kernel_launches += 1;
+    if (!let.ipc_ok) {               // no peer memory: pack, ncclSend / ncclRecv, unpack
+        LET_GROW(sendbuf, (std::max(1, soff[P]))); LET_GROW(recvbuf, (std::max(1, roff[P])));
+        if (soff[P] > 0) {
+            k_let_pack<<<grid_for((int64_t)P * mylen * 32, 256), 256, 0, st>>>(let.table, let.split, let.sendsz, let.sendoff, cd, sk, let.sendbuf);
+            ctr.kernel_launches += 1;
+        }
+        rc = A.GroupStart();
+        for (int q = 0; q < P && rc == bhcomm::kSuccess; ++q) {
+            if (q == rank) continue;
+            const int ns = soff[q + 1] - soff[q], nr = roff[q + 1] - roff[q];
+            if (ns > 0) rc = A.Send(let.sendbuf + soff[q], (size_t)ns * 4, bhcomm::kFloat64, q, comm, st);
+            if (nr > 0 && rc == bhcomm::kSuccess) rc = A.Recv(let.recvbuf + roff[q], (size_t)nr * 4, bhcomm::kFloat64, q, comm, st);
+        }
+        const int rc2 = A.GroupEnd();
+        if (rc == bhcomm::kSuccess) rc = rc2;
+        if (rc != bhcomm::kSuccess) return nccl_fail(rc, "ncclSend/ncclRecv(blocks)");
     }
-    rc = A.GroupStart();
-    for (int q = 0; q < P && rc == bhcomm::kSuccess; ++q) {
-        if (q == rank) continue;
-        const int ns = soff[q + 1] - soff[q], nr = roff[q + 1] - roff[q];
-        if (ns > 0) rc = A.Send(let.sendbuf + soff[q], (size_t)ns * 4, bhcomm::kFloat64, q, comm, st);
-        if (nr > 0 && rc == bhcomm::kSuccess) rc = A.Recv(let.recvbuf + roff[q], (size_t)nr * 4, bhcomm::kFloat64, q, comm, st);
-    }
-    const int rc2 = A.GroupEnd();
-    if (rc == bhcomm::kSuccess) rc = rc2;
-    if (rc != bhcomm::kSuccess) return nccl_fail(rc, "ncclSend/ncclRecv(blocks)");
+    LET_PHASE(8);   // 7: host gap (+ pack, send/recv without peer memory)
     let.last_imported = roff[P]; let.last_sent = soff[P];
     // ---- 7. top tree + blocks + exact climb
     BhTreeView lv{};
     lv.cell = let.cell; lv.cd = let.cd; lv.sk = let.sk; lv.arrived = let.arrived; lv.n_in = let.n_items; lv.M = let.M;
     const BhLetItems it{let.ikey, let.itype, let.iS, let.iW, let.n_items};
-    BH_TRY(cudaMemsetAsync(let.arrived, 0, (size_t)(let.M + 1) * sizeof(int), st));
-    BH_TRY(cudaMemsetAsync(let.dst, 0xFF, (size_t)ncodes * sizeof(int), st));
     if (let.n_items > 0) {
-        k_let_emit<<<grid_for(let.n_items, 256), 256, 0, st>>>(it, let.sk, root.levels, ell, let.ilp, let.dst);
+        k_let_emit<<<grid_for(let.n_items, 256), 256, 0, st>>>(it, let.sk, let.arrived, root.levels, ell, let.ilp, let.dst);
+        LET_PHASE(9);    // 8: top-tree skeletons
         k_let_blocks<<<grid_for((int64_t)ncodes * 32, 256), 256, 0, st>>>(lv, let.table, ncodes, let.split, let.nit, let.blk, let.dst, let.recvoff,
-                                                                          let.recvbuf, cd, sk, root.half);
-    }
+                                                                          let.recvbuf, cd, sk, root.half, let.peers, let.ipc_ok ? 1 : 0);
+    } else LET_PHASE(9);
+    LET_PHASE(10);   // 9: own + imported blocks
     k_let_climb<<<std::max(1, grid_for(let.n_items, 128)), 128, 0, st>>>(lv, root, it, let.table, root.levels, ell, let.ilp);
+    LET_PHASE(11);   // 10: top-tree climb
     if (n_own > 0)
         k_let_leafpos<<<grid_for(n_own, 256), 256, 0, st>>>(n_own, let.lleaf, let.lx, let.ly, root, grid, ell, let.table, let.dst, let.blk, lv, leafpos + lo);
     ctr.kernel_launches += 4;
+    LET_PHASE(12);   // 11: leaf positions
+    LET_PHASE(13); LET_PHASE(14);
+    let.pe_armed = true;
+#undef LET_PHASE
     BH_TRY(cudaEventRecord(ev[slot + 1], st));
     BH_TRY(cudaGetLastError());
     ctr.n_cells = let.M;

@@ -54,7 +54,8 @@ extern "C" {
                                   * summaries + imported boundary subtrees) instead of replicating the
                                   * whole tree; no per-step all-gather of positions.  Bit-identical to
                                   * a single-GPU run; falls back to the replicated tree while the merge
-                                  * rule is enabled.  Env BH_LET=0/1 overrides.                      */
+                                  * rule is enabled and below 4 ranks (BH_LET_MIN_WORLD), where replicating
+                                  * the tree is cheaper.  Env BH_LET=0/1 overrides.                   */
 
 typedef struct bh_engine bh_engine;
 
@@ -250,7 +251,9 @@ int bh_get_counters(bh_engine* e, bh_counters* out);
 int bh_reset_counters(bh_engine* e);
 /* domain-mode statistics (BH_FLAG_LET): out[0..9] = enabled, partition valid, level of the cut,
  * LET evaluations, fallbacks to a re-homing build, cells of this rank's LET, cells imported,
- * cells sent, own strays, items of the top tree (last evaluation). */
+ * cells sent, own strays, items of the top tree (last evaluation); out[10..17] = accumulated
+ * microseconds of the phases of the LET build (segments, guests, local build, summaries +
+ * all-reduce, plan, block exchange, assembly, -). */
 int bh_get_let_stats(bh_engine* e, int64_t* out, int32_t n_out);
 /* per-body counts of the last evaluation (needs BH_FLAG_BODY_COUNTS) */
 int bh_get_body_counts(bh_engine* e, int32_t* interactions, int32_t* opened);

@@ -127,8 +127,10 @@ def test_cuda_nccl_is_bit_identical_to_one_gpu(cuda_lib, tmp_path, merge):
 
 LET_CASES = [
     ("two-disk 40k", lambda: scenes.snap_f32(scenes.default_two_disks(n1=32000, n2=8000, seed=31)), 0.5, 9, 3),
+    ("two-disk 40k, stray overflow -> fallback", lambda: scenes.snap_f32(scenes.default_two_disks(n1=32000, n2=8000, seed=31)), 0.5, 9, 4),
     ("cloud 100k θ0.8", lambda: scenes.snap_f32(scenes.make_uniform_random(100_000, 0.5, seed=32)), 0.8, 6, 2),
     ("two-disk 2k (coarsest cut)", lambda: scenes.snap_f32(scenes.default_two_disks(n1=1500, n2=500, seed=22)), 0.3, 7, 3),
+    ("cloud 100k θ0.5, blocks over ncclSend/ncclRecv", lambda: scenes.snap_f32(scenes.make_uniform_random(100_000, 0.5, seed=33)), 0.5, 5, 2),
 ]
 
 
@@ -146,8 +148,13 @@ def test_cuda_domain_mode_is_bit_identical_to_one_gpu(cuda_lib, tmp_path, name, 
     scene = gen()
     path = str(tmp_path / "scene.npz")
     np.savez(path, x=scene[0], y=scene[1], vx=scene[2], vy=scene[3], m=scene[4], W=2400, H=800, theta=theta)
-    ranks = _run_world(world, "cuda", "nccl", path, str(tmp_path / "out"), steps, 0,
-                       extra_env={"BH_TEST_FLAGS": str(bh_b200.BH_FLAG_LET), "BH_TEST_REHOME": str(rehome)})
+    env = {"BH_TEST_FLAGS": str(bh_b200.BH_FLAG_LET), "BH_TEST_REHOME": str(rehome), "BH_LET_MIN_WORLD": "2"}
+    overflow = "overflow" in name
+    if "ncclSend" in name:
+        env["BH_LET_IPC"] = "0"                # no peer-memory mapping: the packed-block exchange
+    if overflow:
+        env["BH_LET_STRAY_CAP"] = "3"          # more strays than a segment holds: the evaluation is redone after a re-homing
+    ranks = _run_world(world, "cuda", "nccl", path, str(tmp_path / "out"), steps, 0, extra_env=env)
     e = make_engine(cuda_lib, scene, theta=theta, merge_min_dist=0.0)
     e.step(steps)
     single, ctr = e.get_bodies(), e.counters()
@@ -155,6 +162,7 @@ def test_cuda_domain_mode_is_bit_identical_to_one_gpu(cuda_lib, tmp_path, name, 
         for k, nm in enumerate(("x", "y", "vx", "vy", "m")):
             assert (z[nm] == single[k]).all(), nm
         st = dict(zip([str(s) for s in z["let_keys"]], [int(v) for v in z["let"]]))
-        assert st["enabled"] == 1 and st["let_evaluations"] > 0 and st["fallbacks"] == 0, st
+        # enabled: 2 = blocks imported over NVLink peer memory (CUDA IPC), 1 = over ncclSend/ncclRecv
+        assert st["enabled"] == (1 if "ncclSend" in name else 2) and st["let_evaluations"] > 0 and (st["fallbacks"] > 0) == overflow, st
     assert sum(int(z["interactions"]) for z in ranks) == ctr["total_interactions"]
     assert sum(int(z["opened"]) for z in ranks) == ctr["total_opened"]
