@@ -88,6 +88,17 @@ def measured_peaks():
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}, "fallback (B200_PROFILING.md)"
 
 
+_REAL_STDOUT = None
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def run_reference(args, rank, world):
     """The reference's own CPU implementation of the path (JVM unavailable: the literal C++
     port in oracle/) on all host threads, same config/metric as the CUDA arm."""
@@ -121,13 +132,16 @@ def run_reference(args, rank, world):
         "phases_ms_per_step": {"build": c["ms_build"] / args.steps, "walk": c["ms_walk"] / args.steps,
                                "integrate": c["ms_integrate"] / args.steps},
     }
-    print(json.dumps(out), flush=True)
+    emit(out)
 
 
 def main():
-    # NCCL prints a version banner on stdout when NCCL_DEBUG=VERSION; rank 0 must print ONE JSON line
-    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-        os.environ["NCCL_DEBUG"] = "WARN"
+    # rank 0 must print ONE JSON line on stdout: everything libraries print there (NCCL's version banner, ...)
+    # is diverted to stderr; the line itself goes to the saved descriptor
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=None)
@@ -340,7 +354,7 @@ def main():
         }
         if let_stats:
             line["domain_mode_rank0"] = let_stats
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 

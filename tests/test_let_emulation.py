@@ -48,6 +48,15 @@ def _oob_scene():
     return s
 
 
+def _jitter_scene():
+    """coincident bodies (equal keys: the jitter regime of BH.kt:145-156) inside the ranks' own ranges"""
+    s = list(scenes.snap_f32(scenes.make_uniform_random(6000, 0.5, seed=12)))
+    for k in range(0, 60, 3):           # 20 clusters of 3 coincident bodies, spread over the window
+        s[0][k + 1] = s[0][k + 2] = s[0][k]
+        s[1][k + 1] = s[1][k + 2] = s[1][k]
+    return tuple(s)
+
+
 CASES = [
     ("two-disk P2", lambda: scenes.snap_f32(scenes.default_two_disks()), 0.5, 2, 3, 0.0),
     ("two-disk P8", lambda: scenes.snap_f32(scenes.default_two_disks()), 0.5, 8, 5, 0.0),
@@ -59,6 +68,7 @@ CASES = [
     ("n=2", lambda: scenes.make_uniform_random(2, 0.5), 0.5, 2, 2, 0.0),
     ("n=1", lambda: scenes.make_uniform_random(1, 0.5), 0.5, 2, 2, 0.0),
     ("theta=0", lambda: scenes.make_uniform_random(300, 0.5, seed=8), 0.0, 4, 2, 0.0),
+    ("jitter clusters P4", _jitter_scene, 0.5, 4, 3, 0.0),
     ("auto level", lambda: scenes.make_uniform_random(60000, 0.5, seed=9), 0.5, 8, 0, 0.0),
 ]
 
