@@ -349,6 +349,7 @@ def main():
                        "l2": "no flush: per-step working set (~210 B/body state+sort+tree) exceeds the 126 MB L2 and is rewritten every build"},
             "interactions_per_step": inter / args.steps, "opened_per_step": opened / args.steps,
             "phases_ms_per_evaluation": {"build": build_ms, "walk": walk_ms},
+            "ms_per_step_other": {"exchange": c["ms_comm"] / args.steps, "integrate_and_rest": c["ms_integrate"] / args.steps},
             "roofline": roofline, "roofline_build": roofline_build, "cpu_baseline": cpu, "e2e": e2e, "configs0": c1, "reuse_acc_mode": reuse,
             "gpu_launches": launches, "clocks": clocks,
         }
