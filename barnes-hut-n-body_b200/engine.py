@@ -273,10 +273,9 @@ class NativeEngine:
         """Domain-mode (BH_FLAG_LET) statistics of the last evaluation on this rank."""
         v = np.zeros(26, np.int64)
         self._check(self.lib.bh_get_let_stats(self._h, v.ctypes.data_as(C.POINTER(C.c_int64)), 26), "bh_get_let_stats")
+        # [0] 0 = off, 1 = on (blocks over ncclSend/ncclRecv), 2 = on (blocks over NVLink peer memory)
         names = ("enabled", "partition_valid", "cut_level", "let_evaluations", "fallbacks", "let_cells", "cells_imported",
-                 "cells_sent", "own_strays", "top_items", "us_segments", "us_guests", "us_local_build", "us_summaries_allreduce",
-                 "us_plan", "us_block_exchange", "us_assembly", "timed_evaluations", "cpu_us_segments", "cpu_us_guests",
-                 "cpu_us_local_build", "cpu_us_summaries_allreduce", "cpu_us_plan", "cpu_us_block_exchange", "cpu_us_assembly", "cpu_us_spare")
+                 "cells_sent", "own_strays", "top_items")
         return {k: int(x) for k, x in zip(names, v)}
 
     # -- multi-GPU --------------------------------------------------------------------

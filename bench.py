@@ -99,18 +99,51 @@ def emit(line):
         os.write(_REAL_STDOUT, data)
 
 
+REFERENCE_BUDGET_S = 150.0     # CPU time the whole reference arm may take (warm-up + timed steps)
+
+
 def run_reference(args, rank, world):
     """The reference's own CPU implementation of the path (JVM unavailable: the literal C++
-    port in oracle/) on all host threads, same config/metric as the CUDA arm."""
+    port in oracle/) on all host threads, same config/metric as the CUDA arm.  Every step is a
+    full PhysicsEngine.step(); when K + W steps of the whole workload would not fit the time
+    budget, the steps run on a BOUNDED SAMPLE of it: a uniform random subset of the bodies (same
+    window), sized from one calibration step.  The metric is a rate, so it stays comparable."""
     if rank != 0:
         return
     import bh_b200
     lib = bh_b200.bind(os.path.join(ROOT, "oracle", "libbh_ref.so"))
     scene, W, H = workload(max(1, args.gpus), args.bodies)
-    e = bh_b200.NativeEngine(lib=lib)
-    e.set_window(W, H)
-    e.set_params(theta=THETA, merge_min_dist=0.0)
-    e.set_bodies(*scene)
+    n_full = len(scene[0])
+
+    def engine(sc):
+        e = bh_b200.NativeEngine(lib=lib)
+        e.set_window(W, H)
+        e.set_params(theta=THETA, merge_min_dist=0.0)
+        e.set_bodies(*sc)
+        return e
+
+    # calibration: one step on (at most) 250k bodies; a step costs ~ n log n
+    n_cal = min(n_full, 250_000)
+    rng = np.random.default_rng(11)
+    pick = np.sort(rng.choice(n_full, n_cal, replace=False)) if n_cal < n_full else None
+    ec = engine(tuple(a[pick] for a in scene) if pick is not None else scene)
+    t0 = time.perf_counter()
+    ec.step(1)
+    t_cal = time.perf_counter() - t0
+    ec.close()
+    total_steps = args.steps + args.warmup
+    per_body = t_cal / (n_cal * math.log2(max(n_cal, 2)))
+    n_s = n_full
+    while n_s > 20_000 and per_body * n_s * math.log2(n_s) * total_steps > REFERENCE_BUDGET_S - t_cal:
+        n_s = int(n_s * 0.8)
+    if n_s < n_full:
+        pick = np.sort(rng.choice(n_full, n_s, replace=False))
+        scene = tuple(np.ascontiguousarray(a[pick]) for a in scene)
+        sample = (f"{args.steps} full steps on a uniform random subset of {n_s} of the workload's {n_full} bodies "
+                  f"(same window; sized from a {n_cal}-body calibration step to fit {REFERENCE_BUDGET_S:.0f} s)")
+    else:
+        sample = f"{args.steps} full steps of the whole workload"
+    e = engine(scene)
     cores = lib.bh_ref_threads(e._h)
     e.step(args.warmup)
     e.reset_counters()
@@ -124,10 +157,10 @@ def run_reference(args, rank, world):
         "steps_per_s": args.steps / dt, "n_gpus": max(1, args.gpus), "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"{len(scene[0])}-body uniform 'C' cloud, theta={THETA}, {W}x{H} window, G=80, dt=0.005, merge off",
-                   "step": "PhysicsEngine.step(): 2 builds + 2 evaluations + KDK"},
+        "config": {"workload": f"{n_full}-body uniform 'C' cloud, theta={THETA}, {W}x{H} window, G=80, dt=0.005, merge off",
+                   "step": "PhysicsEngine.step(): 2 builds + 2 evaluations + KDK", "bodies_in_the_sample": len(scene[0])},
         "cpu_baseline": {"value": val, "unit": "interactions/s", "cores": int(cores), "kind": "port",
-                         "sample": f"{args.steps} full steps of the same workload (C++ port of BarnesHutAlg.kt; no JVM in the image)"},
+                         "sample": sample + " (C++ port of BarnesHutAlg.kt; no JVM in the image)"},
         "e2e": {"value": val, "unit": "interactions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "phases_ms_per_step": {"build": c["ms_build"] / args.steps, "walk": c["ms_walk"] / args.steps,
                                "integrate": c["ms_integrate"] / args.steps},

@@ -249,11 +249,11 @@ int bh_get_tree(bh_engine* e, int64_t cap, int64_t* n_cells,
 int bh_build_tree(bh_engine* e);
 int bh_get_counters(bh_engine* e, bh_counters* out);
 int bh_reset_counters(bh_engine* e);
-/* domain-mode statistics (BH_FLAG_LET): out[0..9] = enabled, partition valid, level of the cut,
- * LET evaluations, fallbacks to a re-homing build, cells of this rank's LET, cells imported,
- * cells sent, own strays, items of the top tree (last evaluation); out[10..17] = accumulated
- * microseconds of the phases of the LET build (segments, guests, local build, summaries +
- * all-reduce, plan, block exchange, assembly, -). */
+/* domain-mode statistics (BH_FLAG_LET): out[0..9] = mode (0 off, 1 on with blocks over
+ * ncclSend/ncclRecv, 2 on with blocks over NVLink peer memory), partition valid, level of the cut,
+ * LET evaluations, fallbacks to a re-homing build, cells of this rank's LET, cells imported, cells
+ * sent, own strays, items of the top tree (last evaluation).  With BH_LET_TIMERS=1 in the
+ * environment the call also prints this rank's per-phase times to stderr. */
 int bh_get_let_stats(bh_engine* e, int64_t* out, int32_t n_out);
 /* per-body counts of the last evaluation (needs BH_FLAG_BODY_COUNTS) */
 int bh_get_body_counts(bh_engine* e, int32_t* interactions, int32_t* opened);
