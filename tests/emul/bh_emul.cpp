@@ -580,3 +580,41 @@ extern "C" int bh_emul_let(int n, const double* x0, const double* y0, const doub
                  stats[6] = sumLocalM; stats[7] = maxItems; }
     return 0;
 }
+
+// ---- property check of bh_let_near_region: whenever SOME body opens the depth-ELL cell of a candidate
+// (exact f64 test, BH.kt:223-228), the rank's region test must say "near".  Candidates are points; the
+// cell is the level-ELL cell containing the point and the point plays its centre of mass.  Returns the
+// number of violations; out[0] = candidates some body opens, out[1] = candidates reported near.
+extern "C" int bh_emul_let_near_check(int n, const double* x, const double* y, double rcx, double rcy, double rhalf,
+                                      double theta, double soft2, int ell, int ncand, const double* cx, const double* cy,
+                                      int64_t* out) {
+    const BhRoot root{rcx, rcy, rhalf, bh_key_levels(rhalf)};
+    const int L = root.levels, lam = bh_let_lambda(ell);
+    std::vector<uint32_t> bits(((size_t)1 << (2 * lam)) / 32 + 1, 0u);
+    BhLetBox oob{1e300, -1e300, 1e300, -1e300};
+    for (int b = 0; b < n; ++b) {
+        if (!bh_root_contains(root, x[b], y[b])) {
+            oob.x0 = std::min(oob.x0, x[b]); oob.x1 = std::max(oob.x1, x[b]);
+            oob.y0 = std::min(oob.y0, y[b]); oob.y1 = std::max(oob.y1, y[b]);
+        } else {
+            const uint32_t q = bh_let_code(bh_morton_key(root, x[b], y[b]), L, lam);
+            bits[q >> 5] |= 1u << (q & 31u);
+        }
+    }
+    const BhLetRegion reg{bits.data(), oob};
+    const double theta2 = theta * theta;
+    int violations = 0;
+    int64_t opened = 0, near = 0;
+    for (int k = 0; k < ncand; ++k) {
+        if (!bh_root_contains(root, cx[k], cy[k])) continue;
+        const uint32_t c = bh_let_code(bh_morton_key(root, cx[k], cy[k]), L, ell);
+        bool some_opens = false;
+        for (int b = 0; b < n && !some_opens; ++b)
+            some_opens = !bh_exact_accept(cx[k], cy[k], x[b], y[b], soft2, theta2, rhalf, ell);
+        const bool is_near = bh_let_near_region(reg, c, cx[k], cy[k], theta2, soft2, root, ell);
+        opened += some_opens; near += is_near;
+        if (some_opens && !is_near) ++violations;
+    }
+    if (out) { out[0] = opened; out[1] = near; }
+    return violations;
+}

@@ -93,3 +93,28 @@ def test_let_walk_is_bit_identical_to_the_global_tree(emul_lib, name, gen, theta
     assert l[4][3] == 0                                           # no guest inside a jitter cluster
     if theta >= 0.5 and ell == 0:
         assert l[4][4] < g[4][1]                                  # a rank's LET is smaller than the global tree
+
+
+@pytest.mark.parametrize("theta", [0.2, 0.5, 1.0, 1.6])
+@pytest.mark.parametrize("ell", [2, 4, 6])
+def test_region_test_never_misses_a_cell_some_body_opens(emul_lib, theta, ell):
+    """bh_let_near_region is what decides that a remote subtree is NOT imported: it must be conservative
+    with respect to the exact f64 opening test of every body of the rank (bodies outside the root box
+    included), for any level of the cut and any theta."""
+    rng = np.random.default_rng(100 * ell + int(theta * 10))
+    W, H = 2400, 800
+    half = max(W, H) / 2 + 2
+    # a rank's bodies: two clumps, a sparse strip and a few bodies outside the root box
+    x = np.concatenate([rng.normal(600, 60, 300), rng.normal(1900, 20, 200), rng.uniform(0, W, 40), [-500.0, 3000.0, 1200.0]])
+    y = np.concatenate([rng.normal(300, 40, 300), rng.normal(700, 25, 200), rng.uniform(380, 420, 40), [400.0, 400.0, 2500.0]])
+    # candidate cells everywhere, denser around the clumps (where the answer flips)
+    cx = np.concatenate([rng.uniform(-2, 2402, 3000), rng.normal(600, 300, 1500), rng.normal(1900, 200, 1500)])
+    cy = np.concatenate([rng.uniform(-802, 1602, 3000), rng.normal(300, 300, 1500), rng.normal(700, 200, 1500)])
+    x, y, cx, cy = (np.ascontiguousarray(a, np.float64) for a in (x, y, cx, cy))
+    out = np.zeros(2, np.int64)
+    bad = emul_lib.bh_emul_let_near_check(len(x), _dp(x), _dp(y), C.c_double(W / 2), C.c_double(H / 2), C.c_double(half),
+                                          C.c_double(theta), C.c_double(1.0), ell, len(cx), _dp(cx), _dp(cy), out.ctypes.data_as(I64))
+    assert bad == 0
+    assert out[0] > 0 and out[1] >= out[0]            # something is opened; "near" is a superset
+    if theta >= 0.5 and ell >= 4:
+        assert out[1] < len(cx)                       # ... and not everything is near
