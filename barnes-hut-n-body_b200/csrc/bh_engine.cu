@@ -386,6 +386,16 @@ struct bh_engine {
         n_in = sc_host->n_in; n_internal = sc_host->n_internal; M = n_in + n_internal;
         ctr.n_in_tree = n_in; ctr.n_out_of_box = n - n_in; ctr.n_internal = n_internal; ctr.n_cells = M;
         ctr.n_jitter_bodies = sc_host->n_jitter; ctr.max_depth = sc_host->max_depth; ctr.key_levels = root.levels;
+        if (let.local_build && (int64_t)M + 1 > cell_cap) {
+            // Domain mode: the peers map this rank's cell arrays, so a local build must never re-allocate them.
+            // (A local tree has no more cells than the global tree the arrays were sized for; this can only
+            // trigger if the tree grew by > 12 % since the last re-homing.)  Report it: the evaluation is
+            // redone after a re-homing, whose replicated build grows the arrays on every rank alike.
+            let.local_overflow = true;
+            n_in = 0; n_internal = 0; M = 0;
+            jitter_active = false;
+            return BH_OK;
+        }
         BH_RC(ensure_cells((int64_t)M + 1));   // + the terminal record the walk idles on
         if (rehomed && let_usable()) BH_RC(let_partition());   // slices of the new home order, cut at code boundaries
         jitter_active = false;
@@ -545,7 +555,10 @@ struct bh_engine {
         BH_RC(wait_inputs());
         BH_RC(kick(lo, hi, dtHalf, dt, 1));
         if (io_out.armed && io_steps_left == 1) BH_RC(emit_positions_out());
-        if (world > 1) vel_valid = false;
+        if (world > 1) {
+            vel_valid = false;
+            if (transport == T_NCCL) let.pos_valid = false;   // only this rank's slice has drifted here
+        }
         phase = 1;
         return BH_OK;
     }
@@ -575,10 +588,7 @@ struct bh_engine {
         BH_RC(step_begin());
         // the one exchange of the step: drifted positions — not in domain mode, where every rank keeps
         // only its own slice current and the next build exchanges strays and tree blocks instead
-        if (world > 1) {
-            if (let_usable()) let.pos_valid = false;
-            else BH_RC(all_gather_pair(x, y));
-        }
+        if (world > 1 && !let_usable()) BH_RC(sync_positions());
         BH_RC(step_end());
         return step_finish();
     }

@@ -418,6 +418,7 @@ struct bh_let_state {
     int64_t n_declined = -1;     // body count for which let_partition declined (too few bodies)
     BhRoot part_root{};          // root box the partition refers to
     bool local_build = false;    // build() is running on the local arrays
+    bool local_overflow = false; // ... and its tree did not fit the (peer-mapped) cell arrays
     bool view_valid = false;
     int64_t cut[17] = {0};
     LetSplit split{};

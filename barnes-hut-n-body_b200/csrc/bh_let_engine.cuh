@@ -188,6 +188,7 @@ inline int bh_engine::let_evaluate(int slot) {
         const int64_t sn = n;
         x = let.lx; y = let.ly; m = let.lm; perm = let.lperm; leafpos = let.lleaf; n = n_loc;
         let.local_build = true;
+        let.local_overflow = false;
         const int brc = build(slot, false);
         let.local_build = false;
         x = sx; y = sy; m = sm; perm = sperm; leafpos = sleaf; n = sn;
@@ -196,6 +197,7 @@ inline int bh_engine::let_evaluate(int slot) {
     LET_PHASE(4);   // 3: local build
     tree_valid = false;              // the engine's cell arrays hold the LOCAL tree: exports rebuild the global one
     const bool jit = jitter_active;
+    if (let.local_overflow) BH_TRY(cudaMemsetAsync(let.dcnt + LET_D_FLAG, 0x01, sizeof(int), st));   // -> retry flag of this rank
     if (jit && n_in > 0) {
         k_let_jitter_check<<<grid_for(n_in, 256), 256, 0, st>>>(keys_sorted, order, n_in, n_own, let.dcnt + LET_D_FLAG);
         ctr.kernel_launches += 1;
