@@ -37,6 +37,11 @@ object BhNative {
     @JvmStatic external fun bh_num_bodies(e: Pointer): Long
     @JvmStatic external fun bh_get_origin(e: Pointer, cap: Long, origin: IntArray, nOut: LongByReference): Int
     @JvmStatic external fun bh_step(e: Pointer, nsteps: Int): Int
+    /** resetBodies + nsteps x step + getBodies in ONE call, host<->device copies overlapped with the compute
+     *  (merge rule off); the arrays may be null (keep the current bodies / no read-back). */
+    @JvmStatic external fun bh_step_io(e: Pointer, nsteps: Int, nIn: Long, xIn: DoubleArray?, yIn: DoubleArray?, vxIn: DoubleArray?,
+                                       vyIn: DoubleArray?, mIn: DoubleArray?, capOut: Long, xOut: DoubleArray?, yOut: DoubleArray?,
+                                       vxOut: DoubleArray?, vyOut: DoubleArray?, mOut: DoubleArray?, nOut: LongByReference?): Int
     @JvmStatic external fun bh_get_tree(e: Pointer, cap: Long, nCells: LongByReference, cx: DoubleArray?, cy: DoubleArray?,
                                         h: DoubleArray?, mass: DoubleArray?, comx: DoubleArray?, comy: DoubleArray?,
                                         body: IntArray?): Int
