@@ -5,6 +5,10 @@ the tree is replicated, every rank walks and integrates a contiguous slice of th
 ordered) bodies, and the drifted positions are exchanged once per step.  Results are
 bit-identical to a single process because every body's walk sees the same replicated tree.
 
+With ``flags=BH_FLAG_LET`` and the NCCL transport the engine switches, from 4 ranks up, to the DOMAIN
+mode: every rank builds only the tree of its own Morton range and walks a locally essential tree
+ — same results, no replicated build, no per-step all-gather.
+
 Two transports (include/bh_engine.h):
 
 * :func:`init_nccl_engine` — the CUDA engine joins an NCCL communicator itself and

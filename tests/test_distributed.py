@@ -3,8 +3,9 @@
 state is BIT-IDENTICAL to a single-process run on the same inputs.
 
 CPU (`-m "not gpu"`): world_size 2 over gloo, the host-staged transport driving the oracle.
-GPU: the same protocol on the CUDA engine (gloo-staged), and the engine's own NCCL transport
-when the box has >= 2 GPUs."""
+GPU: the same protocol on the CUDA engine (gloo-staged), the engine's own NCCL transport, and the
+DOMAIN mode (BH_FLAG_LET: local trees + locally essential trees, no replicated tree) when the box has
+>= 2 GPUs — always against the same bit-identity bar."""
 import os
 import socket
 import subprocess
