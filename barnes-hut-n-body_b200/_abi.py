@@ -85,6 +85,7 @@ SYMBOLS = {
     "bh_get_bodies": (C.c_int, [_H, C.c_int64, _D, _D, _D, _D, _D, _I64]),
     "bh_num_bodies": (C.c_int64, [_H]),
     "bh_get_origin": (C.c_int, [_H, C.c_int64, _I32, _I64]),
+    "bh_rebase_origin": (C.c_int, [_H]),
     "bh_get_positions_f32": (C.c_int, [_H, C.c_int64, _F, _F, _I64]),
     "bh_default_disk_params": (C.c_int, [C.c_int32, C.c_int32, C.POINTER(BhDiskParams)]),
     "bh_append_disk": (C.c_int, [_H, C.c_int64, C.POINTER(BhDiskParams), C.c_uint64]),
@@ -99,6 +100,7 @@ SYMBOLS = {
     "bh_energy_tree": (C.c_int, [_H, C.c_double, _D, _D, _D, _D]),
     "bh_get_morton": (C.c_int, [_H, _U64, _I32, _I32]),
     "bh_get_tree": (C.c_int, [_H, C.c_int64, _I64, _D, _D, _D, _D, _D, _D, _I32]),
+    "bh_get_tree_root": (C.c_int, [_H, _D, _D, _D, _I64]),
     "bh_build_tree": (C.c_int, [_H]),
     "bh_get_counters": (C.c_int, [_H, C.POINTER(BhCounters)]),
     "bh_reset_counters": (C.c_int, [_H]),

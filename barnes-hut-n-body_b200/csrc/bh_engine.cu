@@ -376,6 +376,7 @@ struct bh_engine {
                 steps_since_rehome = 0;
                 ctr_rehomes++;
                 rehomed = true;
+                acc_valid = false;   // ax/ay are still in the OLD home order (BH_FLAG_REUSE_ACC must not kick with them)
             }
             k_count_scan<<<grid_for(nn, SCAN_TILE), SCAN_THREADS, 0, st>>>(keys_sorted, root.levels, sc(), S, scan_status);
             ctr.kernel_launches += 1;
@@ -406,6 +407,7 @@ struct bh_engine {
             k_jitter<<<grid_for(n_in, 128), 128, 0, st>>>(keys_sorted, const_cast<int*>(order), n_in, root, perm, x, y, jflag, sc());
             ctr.kernel_launches += 1;
             jitter_active = true;
+            acc_valid = false;       // positions were mutated: the accelerations on file belong to the old ones
         }
         if (nn > 0) BH_TRY(cudaMemsetAsync(leafpos, 0xFF, (size_t)nn * sizeof(int), st));   // -1: not in the tree
         if (n_in > 0) {
@@ -873,6 +875,13 @@ int bh_get_origin(bh_engine* e, int64_t cap, int32_t* origin, int64_t* n_out) {
     return BH_OK;
 }
 
+int bh_rebase_origin(bh_engine* e) {
+    if (!e) return BH_E_ARG;
+    if (e->phase != 0) return e->fail(BH_E_STATE, "bh_rebase_origin: a step is in progress");
+    e->origin_identity = true;     // the merge rule re-initialises origin[] from the identity on demand
+    return BH_OK;
+}
+
 int bh_get_positions_f32(bh_engine* e, int64_t cap, float* xy, float* m, int64_t* n_out) {
     if (!e) return BH_E_ARG;
     if (n_out) *n_out = e->n;
@@ -1093,6 +1102,7 @@ int bh_step_io(bh_engine* e, int32_t nsteps, int64_t n_in, const double* x_in, c
         E_TRY(cudaMemcpyAsync(e->hflags, e->dflags, sizeof(int), cudaMemcpyDeviceToHost, e->copy_st));
         E_TRY(cudaEventRecord(e->io_ev[0], e->copy_st));
         e->io_wait_in = true;
+        e->any_zero_mass = true;     // unknown until the flag arrives: the steps use the zero-mass-safe walk
         e->ctr.kernel_launches += 6;
         e->origin_identity = true;
         e->tree_valid = false; e->heavies_valid = false; e->vel_valid = true; e->acc_valid = false;
@@ -1105,6 +1115,14 @@ int bh_step_io(bh_engine* e, int32_t nsteps, int64_t n_in, const double* x_in, c
     e->io_steps_left = 0;
     e->io_out.armed = false;
     if (rc == BH_OK && e->io_wait_in) rc = e->wait_inputs();
+    // the last build of the last step replayed jitter clusters: it mutated x/y AFTER the early read-back
+    // (the reference's buildTree() does, BH.kt:146-151) — send the positions again
+    if (rc == BH_OK && e->jitter_active && (x_out || y_out)) {
+        const cudaError_t cj = cudaStreamSynchronize(e->copy_st);
+        if (cj != cudaSuccess) rc = e->cuda_fail(cj, "bh_step_io");
+        if (rc == BH_OK && x_out) rc = e->download_user(x_out, (const double*)e->x, e->io_stage[0]);
+        if (rc == BH_OK && y_out) rc = e->download_user(y_out, (const double*)e->y, e->io_stage[1]);
+    }
     // ---- (vx, vy) after the last kick
     if (rc == BH_OK) {
         cudaError_t ce = cudaSuccess;
@@ -1246,19 +1264,6 @@ int bh_get_tree(bh_engine* e, int64_t cap, int64_t* n_cells, double* cx, double*
     if (!e) return BH_E_ARG;
     E_TRY(cudaSetDevice(e->device));
     if (!e->tree_valid) E_RC(bh_build_tree(e));   // lastTree ?: buildTree(), BH.kt:329-332
-    if (cap == 1 && e->M > 0) {   // root only (BHTree.mass / comX / comY, BH.kt:103-109): no full export
-        BhCellD r;
-        E_TRY(cudaMemcpy(&r, e->cd, sizeof(BhCellD), cudaMemcpyDeviceToHost));
-        if (cx) cx[0] = e->root.cx;
-        if (cy) cy[0] = e->root.cy;
-        if (h) h[0] = e->root.half;
-        if (mass) mass[0] = r.mass;
-        if (comx) comx[0] = r.comx;
-        if (comy) comy[0] = r.comy;
-        if (body) body[0] = e->M > 1 ? -2 : -3;   // -3: a single body-leaf (index not resolved here)
-        if (n_cells) *n_cells = 1;
-        return BH_OK;
-    }
     try {
         const size_t M = (size_t)e->M, ni = (size_t)e->n_in;
         std::vector<uint64_t> keys(ni);
@@ -1292,6 +1297,19 @@ int bh_get_tree(bh_engine* e, int64_t cap, int64_t* n_cells, double* cx, double*
         if (n_cells) *n_cells = out.count;
         if (cap != 0 && cap < out.count) return e->fail(BH_E_ARG, "bh_get_tree: capacity too small");
     } catch (const std::bad_alloc&) { return e->fail(BH_E_OOM, "bh_get_tree: host out of memory"); }
+    return BH_OK;
+}
+
+int bh_get_tree_root(bh_engine* e, double* mass, double* comx, double* comy, int64_t* n_cells) {
+    if (!e) return BH_E_ARG;
+    E_TRY(cudaSetDevice(e->device));
+    if (!e->tree_valid) E_RC(bh_build_tree(e));   // lastTree ?: buildTree(), BH.kt:329-332
+    BhCellD r; r.comx = e->root.cx; r.comy = e->root.cy; r.mass = 0.0; r.pad = 0.0;   // empty tree: BH.kt:179-183
+    if (e->M > 0) E_TRY(cudaMemcpy(&r, e->cd, sizeof(BhCellD), cudaMemcpyDeviceToHost));
+    if (mass) *mass = r.mass;
+    if (comx) *comx = r.comx;
+    if (comy) *comy = r.comy;
+    if (n_cells) *n_cells = e->M;
     return BH_OK;
 }
 

@@ -71,16 +71,34 @@ inline int bh_engine::merge_rule() {
     BH_TRY(cudaGetLastError());
     const unsigned int n_cand = (unsigned int)hflags[HF_N_CAND];
     if (n_cand == 0) return merge_done();
-    if (n_cand > (unsigned int)nn)
-        return fail(BH_E_UNSUPPORTED, "merge rule: more (heavy, victim) candidate pairs than bodies — merge_max_mass / merge_min_dist make "
-                                      "a large part of the system heavy; not supported on the device");
-
-    // ---- order: heavy rank ascending, victim user index descending; apply sequentially
+    // More (heavy, victim) pairs than bodies (a large part of the system is heavy): the per-body buffers are
+    // too small, so the candidates are listed again into buffers of the reported size.  The SET of pairs is
+    // deterministic (positions do not change during the rule); their order is fixed by the sort below.
+    struct Big {
+        uint64_t *ka = nullptr, *kb = nullptr; uint32_t *va = nullptr, *vb = nullptr, *cand = nullptr, *scr = nullptr;
+        ~Big() { cudaFree(ka); cudaFree(kb); cudaFree(va); cudaFree(vb); cudaFree(cand); cudaFree(scr); }
+    } big;
+    uint64_t *ck_a = keys_a, *ck_b = keys_b;
+    uint32_t *cv_a = vals_a, *cv_b = vals_b, *cscr = sort_scratch();
     int kb = 1;
     while ((1 << kb) < n_heavy) ++kb;
-    const int where = bhsort::onesweep_sort(keys_a, vals_a, keys_b, vals_b, (int64_t)n_cand, 32 + kb, sort_scratch(), st, num_sms);
-    const uint64_t* skeys = where ? keys_b : keys_a;
-    const uint32_t* sslot = where ? vals_b : vals_a;
+    if (n_cand > (unsigned int)nn) {
+        if (n_cand >= (1u << 30)) return fail(BH_E_ARG, "merge rule: more than 2^30 (heavy, victim) candidate pairs");
+        const size_t c = (size_t)n_cand;
+        BH_TRY(dev_alloc(&big.ka, c)); BH_TRY(dev_alloc(&big.kb, c)); BH_TRY(dev_alloc(&big.va, c)); BH_TRY(dev_alloc(&big.vb, c));
+        BH_TRY(dev_alloc(&big.cand, c));
+        BH_TRY(dev_alloc(&big.scr, bhsort::sort_scratch_words((int64_t)c, (32 + kb + 7) / 8)));
+        BH_TRY(cudaMemsetAsync(dflags + HF_N_CAND, 0, sizeof(int), st));
+        k_merge_candidates<<<grid_for(nn, MERGE_TILE), MERGE_TILE, 0, st>>>(x, y, perm, nn, heavy, n_heavy, minD2, big.ka, big.cand,
+                                                                             (int)n_cand, d_count);
+        ctr.kernel_launches += 1;
+        ck_a = big.ka; ck_b = big.kb; cv_a = big.va; cv_b = big.vb; cscr = big.scr; cand_home = big.cand;
+    }
+
+    // ---- order: heavy rank ascending, victim user index descending; apply sequentially
+    const int where = bhsort::onesweep_sort(ck_a, cv_a, ck_b, cv_b, (int64_t)n_cand, 32 + kb, cscr, st, num_sms);
+    const uint64_t* skeys = where ? ck_b : ck_a;
+    const uint32_t* sslot = where ? cv_b : cv_a;
     ctr.kernel_launches += 2 + (32 + kb + 7) / 8;
     BH_TRY(cudaMemsetAsync(dead, 0, (size_t)nn * sizeof(int), st));
     acc_valid = false;   // masses change

@@ -97,13 +97,19 @@ inline int bh_engine::grow_keep(int64_t extra) {
     int* keep_perm = nullptr;
     double** src[5] = {&x, &y, &vx, &vy, &m};
     if (n > 0) {
-        for (int k = 0; k < 5; ++k) {
-            BH_TRY(dev_alloc(&keep[k], (size_t)n));
-            BH_TRY(cudaMemcpyAsync(keep[k], *src[k], (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice, st));
+        cudaError_t ce = cudaSuccess;
+        for (int k = 0; k < 5 && ce == cudaSuccess; ++k) {
+            ce = dev_alloc(&keep[k], (size_t)n);
+            if (ce == cudaSuccess) ce = cudaMemcpyAsync(keep[k], *src[k], (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice, st);
         }
-        BH_TRY(dev_alloc(&keep_perm, (size_t)n));
-        BH_TRY(cudaMemcpyAsync(keep_perm, perm, (size_t)n * sizeof(int), cudaMemcpyDeviceToDevice, st));
-        BH_TRY(cudaStreamSynchronize(st));
+        if (ce == cudaSuccess) ce = dev_alloc(&keep_perm, (size_t)n);
+        if (ce == cudaSuccess) ce = cudaMemcpyAsync(keep_perm, perm, (size_t)n * sizeof(int), cudaMemcpyDeviceToDevice, st);
+        if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);
+        if (ce != cudaSuccess) {           // nothing was changed yet: release the copies and report
+            for (auto& q : keep) cudaFree(q);
+            cudaFree(keep_perm);
+            return cuda_fail(ce, "grow_keep");
+        }
     }
     const int64_t n_keep = n;
     int rc = ensure_bodies(std::max<int64_t>(nn, cap + cap / 2));

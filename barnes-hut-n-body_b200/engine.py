@@ -15,6 +15,7 @@ Paths cited as ``BH.kt:a-b`` are /root/reference/src/main/kotlin/BarnesHutAlg.kt
 from __future__ import annotations
 
 import ctypes as C
+import math
 from dataclasses import dataclass
 from typing import Callable, List, Optional, Sequence
 
@@ -115,6 +116,11 @@ class NativeEngine:
         n_out = C.c_int64()
         self._check(self.lib.bh_get_bodies(self._h, n, *[_dp(a) for a in arrs], C.byref(n_out)), "bh_get_bodies")
         return arrs
+
+    def rebase_origin(self) -> None:
+        """Make the current list the reference list of ``get_origin`` (after the caller has dropped
+        the merged-away ``Body`` objects from its own list, BH.kt:519)."""
+        self._check(self.lib.bh_rebase_origin(self._h), "bh_rebase_origin")
 
     def get_origin(self) -> np.ndarray:
         n = self.n
@@ -246,14 +252,11 @@ class NativeEngine:
 
     def tree_root(self) -> dict:
         """mass / centre of mass of the root cell (BHTree.mass/comX/comY, BH.kt:103-109) without
-        exporting the whole tree."""
-        ncells = C.c_int64()
-        v = {k: np.empty(1, np.float64) for k in ("cx", "cy", "h", "mass", "comx", "comy")}
-        body = np.empty(1, np.int32)
-        rc = self.lib.bh_get_tree(self._h, 1, C.byref(ncells), _dp(v["cx"]), _dp(v["cy"]), _dp(v["h"]),
-                                  _dp(v["mass"]), _dp(v["comx"]), _dp(v["comy"]), _ip(body))
-        self._check(rc, "bh_get_tree")
-        return {k: float(a[0]) for k, a in v.items()}
+        exporting the whole tree; ``n_cells`` = internal + body-leaf cells."""
+        v = [C.c_double(), C.c_double(), C.c_double()]
+        k = C.c_int64()
+        self._check(self.lib.bh_get_tree_root(self._h, C.byref(v[0]), C.byref(v[1]), C.byref(v[2]), C.byref(k)), "bh_get_tree_root")
+        return {"mass": v[0].value, "comx": v[1].value, "comy": v[2].value, "n_cells": int(k.value)}
 
     def counters(self) -> dict:
         c = BhCounters()
@@ -390,14 +393,86 @@ class Quad:
         return Quad(self.cx + hh, self.cy + hh, hh)
 
 
+class Acc:
+    """BH.kt:33-41 — per-worker force accumulator."""
+    __slots__ = ("fx", "fy")
+
+    def __init__(self):
+        self.fx = 0.0
+        self.fy = 0.0
+
+    def reset(self):
+        self.fx = 0.0
+        self.fy = 0.0
+
+
 class BHTree:
     """Read-only host view of the device quadtree (BH.kt:95-275).
 
     The tree lives on the GPU as a flattened preorder array; this view holds the export
-    of ``bh_get_tree`` (all cells incl. empty leaves, ``visitQuads`` order)."""
+    of ``bh_get_tree`` (all cells incl. empty leaves, ``visitQuads`` order; ``body[k]`` = index of
+    the body in a leaf, -1 empty leaf, -2 internal cell, which always has 4 children)."""
 
-    def __init__(self, cells: dict):
+    def __init__(self, cells: dict, bodies: Optional[List["Body"]] = None):
         self._c = cells
+        self._bodies = bodies
+
+    def insert(self, b: "Body"):   # BH.kt:125-137
+        raise NotImplementedError("BHTree is a read-only view of the device tree (built from the engine's body list, "
+                                  "BH.kt:359-366); use PhysicsEngine.resetBodies(old + new)")
+
+    def computeMass(self):          # BH.kt:173-202: masses / centres of mass arrive computed (bit-identical f64)
+        return None
+
+    def accumulateForce(self, b: "Body", theta2: float, acc: Acc) -> None:
+        """BH.kt:215-239 in f64 over the exported cells, same expression order (diagnostics / tests).
+        `b` is skipped by identity (BH.kt:219) when the view knows the engine's body list."""
+        c = self._c
+        body, mass, comx, comy, h = c["body"], c["mass"], c["comx"], c["comy"], c["h"]
+        if len(body) == 0:
+            return
+        soft2, G = Config.SOFT2, Config.G
+        bodies = self._bodies
+
+        def skip(p):
+            if body[p] != -2:
+                return p + 1
+            q = p + 1
+            for _ in range(4):
+                q = skip(q)
+            return q
+
+        def point(px, py, m):       # BH.kt:250-259
+            dx = px - b.x
+            dy = py - b.y
+            r2 = dx * dx + dy * dy + soft2
+            invR = 1.0 / math.sqrt(r2)
+            invR2 = 1.0 / r2
+            f = G * b.m * m * invR2
+            acc.fx += f * dx * invR
+            acc.fy += f * dy * invR
+
+        def walk(p):
+            if mass[p] == 0.0:      # BH.kt:216
+                return skip(p)
+            if body[p] != -2:       # leaf, BH.kt:218-221
+                k = int(body[p])
+                if k >= 0 and not (bodies is not None and bodies[k] is b):
+                    point(float(comx[p]), float(comy[p]), float(mass[p]))
+                return p + 1
+            dx = float(comx[p]) - b.x
+            dy = float(comy[p]) - b.y
+            dist2 = dx * dx + dy * dy + soft2
+            side = float(h[p]) * 2.0
+            if side * side < theta2 * dist2:
+                point(float(comx[p]), float(comy[p]), float(mass[p]))
+                return skip(p)
+            q = p + 1
+            for _ in range(4):
+                q = walk(q)
+            return q
+
+        walk(0)
 
     @property
     def mass(self) -> float:   # BH.kt:103
@@ -454,13 +529,14 @@ class PhysicsEngine:
         x, y, vx, vy, m = self._native.get_bodies()
         origin = self._native.get_origin()
         bs = self._bodies
-        if len(origin) != len(bs):   # the merge rule removed bodies (BH.kt:514-520)
+        n_before = len(bs)
+        if len(origin) != n_before:  # the merge rule removed bodies (BH.kt:514-520)
             keep = [bs[k] for k in origin.tolist()]
             bs[:] = keep             # same list object, like bodies.removeAt
         for b, xi, yi, vxi, vyi, mi in zip(bs, x.tolist(), y.tolist(), vx.tolist(), vy.tolist(), m.tolist()):
             b.x, b.y, b.vx, b.vy, b.m = xi, yi, vxi, vyi, mi
-        if len(origin) and (origin != np.arange(len(origin), dtype=np.int32)).any():
-            self._upload()           # re-base origin onto the shrunk list
+        if len(origin) != n_before:
+            self._native.rebase_origin()   # origin[] now indexes the shrunk list (nothing is re-uploaded)
 
     # -- public API -------------------------------------------------------------------
     def getTreeForDebug(self) -> BHTree:            # BH.kt:329-332
@@ -468,7 +544,7 @@ class PhysicsEngine:
             self._push_config()
             # bh_get_tree exports the tree cached by the last step, or builds a fresh
             # one if a reset/merge dropped it — exactly `lastTree ?: buildTree()`.
-            self._lastTree = BHTree(self._native.tree())
+            self._lastTree = BHTree(self._native.tree(), self._bodies)
         return self._lastTree
 
     def getBodies(self) -> List[Body]:              # BH.kt:335

@@ -152,6 +152,11 @@ int64_t bh_num_bodies(const bh_engine* e);
  * position k.  Identity until the merge rule (BarnesHutAlg.kt:514-520) removes
  * bodies; lets a façade write state back into the SAME Body objects the UI holds. */
 int bh_get_origin(bh_engine* e, int64_t cap, int32_t* origin, int64_t* n_out);
+/* Declare the CURRENT list the new reference list: afterwards bh_get_origin is the identity again.
+ * A façade calls it after it has removed the merged-away Body objects from its own list
+ * (bodies.removeAt, BarnesHutAlg.kt:519), so that the next step's origin[] indexes the shrunk
+ * list.  Nothing is copied and the device state is untouched. */
+int bh_rebase_origin(bh_engine* e);
 /* render read-back used by NBodyPanel.paintComponent (NBodyPanel.kt:302-306):
  * interleaved float (x,y) pairs and float masses. */
 int bh_get_positions_f32(bh_engine* e, int64_t cap, float* xy, float* m, int64_t* n_out);
@@ -245,6 +250,10 @@ int bh_get_morton(bh_engine* e, uint64_t* key, int32_t* depth, int32_t* order);
 int bh_get_tree(bh_engine* e, int64_t cap, int64_t* n_cells,
                 double* cx, double* cy, double* h,
                 double* mass, double* comx, double* comy, int32_t* body);
+/* BHTree.mass / comX / comY of the ROOT (BarnesHutAlg.kt:103-109) without exporting the tree
+ * (an empty tree reports mass 0 at the root centre, :179-183); *n_cells = internal + body-leaf
+ * cells of the device tree.  Builds the tree if none is cached (:329-332). */
+int bh_get_tree_root(bh_engine* e, double* mass, double* comx, double* comy, int64_t* n_cells);
 /* buildTree() only (BarnesHutAlg.kt:359-366); what getTreeForDebug() triggers. */
 int bh_build_tree(bh_engine* e);
 int bh_get_counters(bh_engine* e, bh_counters* out);

@@ -8,7 +8,20 @@ import com.sun.jna.*
 import com.sun.jna.ptr.*
 
 data class Body(var x: Double, var y: Double, var vx: Double, var vy: Double, var m: Double)
-data class Quad(val cx: Double, val cy: Double, val h: Double)
+data class Quad(val cx: Double, val cy: Double, val h: Double) {
+    /** half-open box test, BarnesHutAlg.kt:61-62 */
+    fun contains(b: Body): Boolean = b.x >= cx - h && b.x < cx + h && b.y >= cy - h && b.y < cy + h
+    /** 0 = NW, 1 = NE, 2 = SW, 3 = SE, BarnesHutAlg.kt:73-81 */
+    fun child(which: Int): Quad {
+        val hh = h / 2.0
+        return when (which) {
+            0 -> Quad(cx - hh, cy - hh, hh)
+            1 -> Quad(cx + hh, cy - hh, hh)
+            2 -> Quad(cx - hh, cy + hh, hh)
+            else -> Quad(cx + hh, cy + hh, hh)
+        }
+    }
+}
 
 @Structure.FieldOrder("struct_size", "device", "threads", "flags", "capacity_hint", "rehome_interval", "reserved")
 class BhConfig : Structure() {
@@ -36,6 +49,7 @@ object BhNative {
                                           vy: DoubleArray, m: DoubleArray, nOut: LongByReference): Int
     @JvmStatic external fun bh_num_bodies(e: Pointer): Long
     @JvmStatic external fun bh_get_origin(e: Pointer, cap: Long, origin: IntArray, nOut: LongByReference): Int
+    @JvmStatic external fun bh_rebase_origin(e: Pointer): Int
     @JvmStatic external fun bh_step(e: Pointer, nsteps: Int): Int
     /** resetBodies + nsteps x step + getBodies in ONE call, host<->device copies overlapped with the compute
      *  (merge rule off); the arrays may be null (keep the current bodies / no read-back). */
@@ -47,13 +61,50 @@ object BhNative {
                                         body: IntArray?): Int
 }
 
-/** Host view of the device quadtree: visitQuads order incl. empty leaves (BarnesHutAlg.kt:265-274). */
+/** Per-worker force accumulator, BarnesHutAlg.kt:33-41. */
+class Acc { var fx = 0.0; var fy = 0.0; fun reset() { fx = 0.0; fy = 0.0 } }
+
+/** Host view of the device quadtree: visitQuads order incl. empty leaves (BarnesHutAlg.kt:265-274).
+ *  body[k] = index of the body in a leaf, -1 empty leaf, -2 internal cell (which always has 4 children). */
 class BHTree(private val cx: DoubleArray, private val cy: DoubleArray, private val h: DoubleArray,
-             massArr: DoubleArray, comxArr: DoubleArray, comyArr: DoubleArray) {
+             private val massArr: DoubleArray, private val comxArr: DoubleArray, private val comyArr: DoubleArray,
+             private val body: IntArray, private val bodies: List<Body>) {
     val mass = massArr.firstOrNull() ?: 0.0
     val comX = comxArr.firstOrNull() ?: 0.0
     val comY = comyArr.firstOrNull() ?: 0.0
     fun visitQuads(visit: (Quad) -> Unit) { for (i in cx.indices) visit(Quad(cx[i], cy[i], h[i])) }
+
+    /** The tree is built on the device from the engine's body list (BarnesHutAlg.kt:359-366): a host-side insert
+     *  into this read-only view would not be seen by step().  Use PhysicsEngine.resetBodies(old + new). */
+    fun insert(b: Body): Nothing = throw UnsupportedOperationException("BHTree is a read-only view; use PhysicsEngine.resetBodies")
+    /** Masses and centres of mass arrive computed (bit-identical to BarnesHutAlg.kt:173-202). */
+    fun computeMass() {}
+
+    /** BarnesHutAlg.kt:215-239 over the exported cells (f64, same expression order): for diagnostics / tests. */
+    fun accumulateForce(b: Body, theta2: Double, acc: Acc) { if (cx.isNotEmpty()) walk(0, b, theta2, acc) }
+    private fun walk(p: Int, b: Body, theta2: Double, acc: Acc): Int {      // returns the position after the subtree
+        val internal = body[p] == -2
+        if (massArr[p] == 0.0) return skip(p)                                // :216
+        if (!internal) {                                                      // :218-221
+            if (body[p] >= 0 && bodies[body[p]] !== b) point(b, comxArr[p], comyArr[p], massArr[p], acc)
+            return p + 1
+        }
+        val dx = comxArr[p] - b.x; val dy = comyArr[p] - b.y
+        val dist2 = dx * dx + dy * dy + Config.SOFT2                          // :223-225
+        val side = h[p] * 2.0
+        if (side * side < theta2 * dist2) { point(b, comxArr[p], comyArr[p], massArr[p], acc); return skip(p) }
+        var q = p + 1
+        repeat(4) { q = walk(q, b, theta2, acc) }                             // :233-237
+        return q
+    }
+    private fun skip(p: Int): Int { if (body[p] != -2) return p + 1; var q = p + 1; repeat(4) { q = skip(q) }; return q }
+    private fun point(b: Body, px: Double, py: Double, m: Double, acc: Acc) { // :250-259
+        val dx = px - b.x; val dy = py - b.y
+        val r2 = dx * dx + dy * dy + Config.SOFT2
+        val invR = 1.0 / kotlin.math.sqrt(r2); val invR2 = 1.0 / r2
+        val f = Config.G * b.m * m * invR2
+        acc.fx += f * dx * invR; acc.fy += f * dy * invR
+    }
 }
 
 class PhysicsEngine(initialBodies: MutableList<Body>) {
@@ -89,11 +140,15 @@ class PhysicsEngine(initialBodies: MutableList<Body>) {
         val origin = IntArray(n); val nOut = LongByReference()
         ck(BhNative.bh_get_bodies(e, n.toLong(), x, y, vx, vy, m, nOut))
         ck(BhNative.bh_get_origin(e, n.toLong(), origin, nOut))
-        if (n != bodies.size) {            // merge rule removed bodies, BarnesHutAlg.kt:514-520
+        val shrunk = n != bodies.size
+        if (shrunk) {                      // merge rule removed bodies, BarnesHutAlg.kt:514-520: drop the same objects
             val keep = origin.map { bodies[it] }
-            bodies.clear(); bodies.addAll(keep); upload()
+            bodies.clear(); bodies.addAll(keep)
         }
+        // write the t+dt state (and the grown masses) into the surviving objects FIRST ...
         for (i in 0 until n) { val b = bodies[i]; b.x = x[i]; b.y = y[i]; b.vx = vx[i]; b.vy = vy[i]; b.m = m[i] }
+        // ... then tell the engine that origin[] now indexes the shrunk list; nothing is re-uploaded
+        if (shrunk) ck(BhNative.bh_rebase_origin(e))
     }
 
     fun getBodies(): List<Body> = bodies
@@ -105,8 +160,8 @@ class PhysicsEngine(initialBodies: MutableList<Body>) {
         ck(BhNative.bh_get_tree(e, 0, nc, null, null, null, null, null, null, null))
         val k = nc.value.toInt()
         val cx = DoubleArray(k); val cy = DoubleArray(k); val h = DoubleArray(k)
-        val ms = DoubleArray(k); val qx = DoubleArray(k); val qy = DoubleArray(k)
-        ck(BhNative.bh_get_tree(e, k.toLong(), nc, cx, cy, h, ms, qx, qy, null))
-        BHTree(cx, cy, h, ms, qx, qy).also { lastTree = it }
+        val ms = DoubleArray(k); val qx = DoubleArray(k); val qy = DoubleArray(k); val bi = IntArray(k)
+        ck(BhNative.bh_get_tree(e, k.toLong(), nc, cx, cy, h, ms, qx, qy, bi))
+        BHTree(cx, cy, h, ms, qx, qy, bi, bodies).also { lastTree = it }
     }
 }

@@ -489,6 +489,12 @@ int bh_get_origin(bh_engine* e, int64_t cap, int32_t* origin, int64_t* n_out) {
     return BH_OK;
 }
 
+int bh_rebase_origin(bh_engine* e) {
+    if (!e) return BH_E_ARG;
+    for (size_t i = 0; i < e->origin.size(); ++i) e->origin[i] = (int32_t)i;
+    return BH_OK;
+}
+
 int bh_get_positions_f32(bh_engine* e, int64_t cap, float* xy, float* m, int64_t* n_out) {
     if (!e) return BH_E_ARG;
     const int64_t n = (int64_t)e->bodies.size();
@@ -713,6 +719,25 @@ int bh_get_tree(bh_engine* e, int64_t cap, int64_t* n_cells, double* cx, double*
         if (n_cells) *n_cells = k;
         if (cap != 0 && cap < k) return fail(e, BH_E_ARG, "bh_get_tree: capacity too small");
     } catch (const std::bad_alloc&) { return fail(e, BH_E_OOM, "bh_get_tree: out of memory"); }
+    return BH_OK;
+}
+
+int bh_get_tree_root(bh_engine* e, double* mass, double* comx, double* comy, int64_t* n_cells) {
+    if (!e) return BH_E_ARG;
+    try {
+        const BHTree* root = e->getTreeForDebug();      // BH.kt:329-332
+        if (mass) *mass = root->mass;                   // BH.kt:103-109
+        if (comx) *comx = root->comX;
+        if (comy) *comy = root->comY;
+        if (n_cells) {                                  // internal + body-leaf cells (empty leaves are implicit on the device)
+            int64_t k = 0;
+            struct Rec { static void go(const BHTree* t, int64_t& k) {
+                if (t->children) { ++k; for (int c = 0; c < 4; ++c) go(&t->children[c], k); }
+                else if (t->body) ++k; } };
+            Rec::go(root, k);
+            *n_cells = k;
+        }
+    } catch (const std::bad_alloc&) { return fail(e, BH_E_OOM, "bh_get_tree_root: out of memory"); }
     return BH_OK;
 }
 
