@@ -58,7 +58,9 @@ class BhCounters(C.Structure):
                 ("total_evaluations", C.c_int64), ("total_steps", C.c_int64), ("total_merged", C.c_int64),
                 ("ms_build", C.c_double), ("ms_walk", C.c_double), ("ms_integrate", C.c_double),
                 ("ms_merge", C.c_double), ("ms_comm", C.c_double),
-                ("ms_step_call", C.c_double), ("kernel_launches", C.c_int64)]
+                ("ms_step_call", C.c_double), ("kernel_launches", C.c_int64),
+                ("bbox_min_x", C.c_double), ("bbox_max_x", C.c_double), ("bbox_min_y", C.c_double), ("bbox_max_y", C.c_double),
+                ("ms_direct", C.c_double)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -115,6 +117,8 @@ SYMBOLS = {
     "bh_step_finish": (C.c_int, [_H]),
     "bh_export_slice": (C.c_int, [_H, C.c_int32, C.c_int64, _D, _D, _I64, _I64]),
     "bh_import_slices": (C.c_int, [_H, C.c_int32, C.c_int64, _D, _D]),
+    "bh_evaluate_slice": (C.c_int, [_H, C.c_int64, _D, _D, _I32, _I64]),
+    "bh_set_domain_mode": (C.c_int, [_H, C.c_int32]),
     "bh_measure_fp32_tflops": (C.c_int, [C.c_int32, _D]),
 }
 

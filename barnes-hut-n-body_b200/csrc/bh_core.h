@@ -510,20 +510,7 @@ BH_HD BhWalkParams bh_walk_params(double theta, double soft2, double half) {
 
 struct BhWalkResult { double ax, ay; int interactions, opened, retests; };
 
-#ifndef BH_WALK_NEWTON
-#define BH_WALK_NEWTON 1      // one Newton step on MUFU.RSQ (device only)
-#endif
 #define BH_WALK_CHUNK 16      // visits between two folds of the FP32 partial sums into f64
-
-#if defined(__CUDACC__)
-// one 256-bit load of a whole 32-byte cell record (sm_100: LDG.E.256): one L1 wavefront per
-// distinct line instead of two
-__device__ __forceinline__ void bh_load_cell(const BhCell* __restrict__ c, float4* a, float4* b) {
-    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                 : "=f"(a->x), "=f"(a->y), "=f"(a->z), "=f"(a->w), "=f"(b->x), "=f"(b->y), "=f"(b->z), "=f"(b->w)
-                 : "l"(c));
-}
-#endif
 
 // The reference's f64 opening test for a borderline cell (cold path), BH.kt:223-228 bit-for-bit.
 BH_HD_COLD bool bh_retest_cell(const BhCellD* __restrict__ cd, const BhCellS* __restrict__ sk, int p, double x, double y,
@@ -531,95 +518,21 @@ BH_HD_COLD bool bh_retest_cell(const BhCellD* __restrict__ cd, const BhCellS* __
     return bh_exact_accept(cd[p].comx, cd[p].comy, x, y, soft2, theta2, half, sk[p].level);
 }
 
-#if BH_WALK_NEWTON
-#define BH_WALK_NEWTON_ASM                                                                      \
-    "mul.f32 t2, inv, inv;\n\t"                                                                 \
-    "fma.rn.f32 t1, %7, t2, 0fC0400000;\n\t" /* d2*inv^2 - 3 */                                 \
-    "mul.f32 inv, inv, t1;\n\t"              /* -2 * refined rsqrt */
-#else
-#define BH_WALK_NEWTON_ASM ""
-#endif
-// second half of a visit: operands  %0 fx  %1 fy  %2 interactions  %3 opened  %4 p  |  %5 t  %6 self
-// %7 d2  %8 m  %9 dx  %10 dy  %11 skip
-#define BH_WALK_VISIT_ASM()                                                                     \
-    asm volatile(                                                                               \
-        "{\n\t"                                                                                 \
-        ".reg .pred P0, P1;\n\t"                                                                \
-        ".reg .f32 inv, t1, t2, wg;\n\t"                                                        \
-        ".reg .s32 p1;\n\t"                                                                     \
-        "setp.gt.f32 P0, %5, 0f00000000;\n\t"          /* accept                          */    \
-        "setp.ne.and.s32 P1, %4, %6, P0;\n\t"          /* ... and not the body's own leaf */    \
-        "setp.neu.and.f32 P1, %8, 0f00000000, P1;\n\t" /* ... and mass != 0 (BH.kt:216)   */    \
-        "rsqrt.approx.ftz.f32 inv, %7;\n\t"                                                     \
-        BH_WALK_NEWTON_ASM                                                                      \
-        "mul.f32 wg, %8, inv;\n\t"                                                              \
-        "mul.f32 wg, wg, inv;\n\t"                                                              \
-        "mul.f32 wg, wg, inv;\n\t"                                                              \
-        "@P1 fma.rn.f32 %0, wg, %9, %0;\n\t"                                                    \
-        "@P1 fma.rn.f32 %1, wg, %10, %1;\n\t"                                                   \
-        "@P1 add.s32 %2, %2, 1;\n\t"                                                            \
-        "@!P0 add.s32 %3, %3, 1;\n\t"                                                           \
-        "add.s32 p1, %4, 1;\n\t"                                                                \
-        "selp.s32 %4, %11, p1, P0;\n\t"                                                         \
-        "}"                                                                                     \
-        : "+f"(fx), "+f"(fy), "+r"(ni), "+r"(no), "+r"(p)                                       \
-        : "f"(tt), "r"(self), "f"(d2), "f"(a.z), "f"(dx), "f"(dy), "r"(__float_as_int(b.z)))
-
-// accumulateForce (BH.kt:215-239) for one body, stackless over the preorder array.
-// `self` = preorder position of the body's own leaf (-1 if it is not in the tree).
-// Per-body decisions are the reference's: the FP32 test t = theta^2 d^2 - s^2 > 0 decides unless
-// |t| is inside the cell's guard band, where the exact f64 expression decides.  Interaction math
-// is FP32 on (hi,lo)-split coordinate differences; FP32 partial sums are folded into f64
-// accumulators every BH_WALK_CHUNK visits.  Returns sum m*d/r^3 (G is applied by the caller).
-//
-// Device form.  Every lane of the warp must call this (`active` = false for surplus lanes).  A
-// visit is branch-free apart from the rare f64 re-test (an opened cell simply does not
-// accumulate), so lanes that disagree on accept/open do not serialise; a lane that has finished
-// idles on the terminal record cell[M] (mass 0, always accepted, skip = M) until the whole warp
-// is done, so there is no per-visit exit test either.  One visit is ~31 SASS instructions: one
-// 256-bit load, 6 FADD + 2 FFMA for the split difference and d^2, FFMA + 2 FSETP for the test,
-// MUFU.RSQ + one Newton step written as ic = inv*(d2*inv^2 - 3) (= -2 x the refined 1/sqrt; the
-// factor (-2)^3 is divided out exactly at the end), 3 FMUL for m*ic^3, predicated accumulation
-// and counters, and the skip/next select.
-BH_HD BhWalkResult bh_walk_body(const BhTreeView& t, const BhWalkParams& w, double x, double y, int self, bool active,
-                                int zero = 0) {
+// accumulateForce (BH.kt:215-239) for one body, stackless over the preorder array: the HOST form (CPU
+// emulation of the device walk, tests only).  `self` = preorder position of the body's own leaf (-1 if it
+// is not in the tree).  Per-body decisions are the reference's: the FP32 test t = theta^2 d^2 - s^2 > 0
+// decides unless |t| is inside the cell's guard band, where the exact f64 expression decides.
+// Interaction math is FP32 on (hi,lo)-split coordinate differences; FP32 partial sums are folded into
+// f64 accumulators every BH_WALK_CHUNK visits.  Returns sum m*d/r^3 (G is applied by the caller).
+BH_HD BhWalkResult bh_walk_body(const BhTreeView& t, const BhWalkParams& w, double x, double y, int self, bool active) {
     float xh, xl, yh, yl;
     bh_split(x, &xh, &xl);
     bh_split(y, &yh, &yl);
-    BH_OPAQUE_F(xh); BH_OPAQUE_F(xl); BH_OPAQUE_F(yh); BH_OPAQUE_F(yl);   // keep the F2F out of the loop
     BhWalkResult r; r.ax = 0.0; r.ay = 0.0; r.interactions = 0; r.opened = 0; r.retests = 0;
     const float th2 = w.th2f, soft2 = w.soft2f;
     const BhCell* __restrict__ cells = t.cell;
     const int M = t.M;
     int p = active ? 0 : M;
-#if defined(__CUDA_ARCH__)
-    // `zero` is a 0 the compiler cannot see through (loaded from memory): it keeps the base
-    // pointer in registers instead of re-loading it from the constant bank at every visit
-    cells += zero;
-    int ni = 0, no = 0;
-    while (__any_sync(0xffffffffu, p < M)) {
-        float fx = 0.f, fy = 0.f;
-#pragma unroll
-        for (int k = 0; k < BH_WALK_CHUNK; ++k) {
-            float4 a, b;
-            bh_load_cell(cells + p, &a, &b);
-            const float dx = (a.x - xh) + (b.x - xl);
-            const float dy = (a.y - yh) + (b.y - yl);
-            const float d2 = fmaf(dx, dx, fmaf(dy, dy, soft2));
-            float tt = fmaf(d2, th2, -a.w);
-            if (fabsf(tt) <= b.w) {   // borderline: the reference's f64 test decides
-                tt = bh_retest_cell(t.cd, t.sk, p, x, y, w.soft2, w.theta2, w.half) ? 1.0f : -1.0f;
-                r.retests++;
-            }
-            BH_WALK_VISIT_ASM();
-        }
-        r.ax += (double)fx; r.ay += (double)fy;
-    }
-    r.interactions = ni; r.opened = no;
-#if BH_WALK_NEWTON
-    r.ax *= -0.125; r.ay *= -0.125;   // (-2)^3 from the Newton form above; exact (power of two)
-#endif
-#else
     while (p < M) {
         float fx = 0.f, fy = 0.f;
         for (int k = 0; k < BH_WALK_CHUNK; ++k) {
@@ -645,7 +558,6 @@ BH_HD BhWalkResult bh_walk_body(const BhTreeView& t, const BhWalkParams& w, doub
         }
         r.ax += (double)fx; r.ay += (double)fy;
     }
-#endif
     return r;
 }
 
@@ -656,100 +568,230 @@ BH_HD void bh_write_terminal_cell(const BhTreeView& t) {
     t.cell[t.M] = c;
 }
 
-// ---- lane-group walk: LG adjacent lanes (= LG Morton-adjacent bodies) share ONE position ---------
-// The per-lane walk is bound by the L1 data stage: the 32 lanes of a warp are at ~15 different
-// cells per iteration and every distinct sector costs a data-stage cycle.  Here the LG lanes of a
-// group walk in lockstep: a cell is opened when ANY un-muted lane of the group opens it; a lane
-// that accepts a cell its group opens takes the interaction and is muted (`mute` = skip of that
-// cell) until the walk leaves the subtree.  Per-body decisions — the set and order of each body's
-// interactions — are exactly those of the per-lane walk; a warp now touches at most 32/LG
-// sectors per iteration at the price of the union of the group's cells (probe
-// bh_emul_group_stats: 1.24x the iterations for LG = 4) and ~7 instructions of group logic.
-// second half of a visit: operands  %0 fx  %1 fy  %2 interactions  %3 opened  %4 p  %5 mute  |
-// %6 t  %7 self  %8 d2  %9 m  %10 dx  %11 dy  %12 skip  %13 shift of the group's bits in a ballot
-#define BH_LANEGROUP_VISIT_ASM()                                                                \
-    asm volatile(                                                                               \
-        "{\n\t"                                                                                 \
-        ".reg .pred Pu, P0, Pw, Pg, P1;\n\t"                                                    \
-        ".reg .f32 te, inv, t1, t2, wg;\n\t"                                                    \
-        ".reg .b32 bal;\n\t"                                                                    \
-        ".reg .s32 p1;\n\t"                                                                     \
-        "setp.ge.s32 Pu, %4, %5;\n\t"                  /* un-muted                         */   \
-        "selp.f32 te, %6, 0f7FC00000, Pu;\n\t"         /* muted: neither accepts nor opens */   \
-        "setp.gt.f32 P0, te, 0f00000000;\n\t"          /* accepts                          */   \
-        "setp.lt.f32 Pw, te, 0f00000000;\n\t"          /* wants the cell opened            */   \
-        "vote.sync.ballot.b32 bal, Pw, 0xffffffff;\n\t"                                         \
-        "shr.b32 bal, bal, %13;\n\t"                                                            \
-        "and.b32 bal, bal, %14;\n\t"                                                            \
-        "setp.ne.u32 Pg, bal, 0;\n\t"                  /* some lane of MY group opens it   */   \
-        "setp.ne.and.s32 P1, %4, %7, P0;\n\t"          /* ... not the body's own leaf      */   \
-        "setp.neu.and.f32 P1, %9, 0f00000000, P1;\n\t" /* ... and mass != 0 (BH.kt:216)    */   \
-        "rsqrt.approx.ftz.f32 inv, %8;\n\t"                                                     \
-        BH_LANEGROUP_NEWTON_ASM                                                                 \
-        "mul.f32 wg, %9, inv;\n\t"                                                              \
-        "mul.f32 wg, wg, inv;\n\t"                                                              \
-        "mul.f32 wg, wg, inv;\n\t"                                                              \
-        "@P1 fma.rn.f32 %0, wg, %10, %0;\n\t"                                                   \
-        "@P1 fma.rn.f32 %1, wg, %11, %1;\n\t"                                                   \
-        "@P1 add.s32 %2, %2, 1;\n\t"                                                            \
-        "@Pw add.s32 %3, %3, 1;\n\t"                                                            \
-        "@P0 mov.s32 %5, %12;\n\t"                     /* muted until the walk leaves the cell */ \
-        "add.s32 p1, %4, 1;\n\t"                                                                \
-        "selp.s32 %4, p1, %12, Pg;\n\t"                                                         \
+#if defined(__CUDACC__)
+// ---- the DEVICE walk: G Morton-consecutive bodies per thread, one shared preorder position ---------
+// ncu on the one-body-per-lane walk of round 1 (profiles/r01c): the L1 data stage is the limiter, not
+// the issue slots — the 32 lanes of a warp sit at ~15 different cells, and every distinct 32 B sector
+// of a warp-wide load costs a data-stage cycle (15 cycles per warp iteration against 35 issue slots
+// shared by 4 schedulers).  Here a THREAD walks for G bodies at once: the record is loaded once and
+// tested against the G bodies, so a warp-wide load serves 32*G body visits and the G independent
+// dependency chains give the scheduler instruction-level parallelism.
+//
+// Per-body decisions stay the reference's (BH.kt:223-228 is evaluated per body): a cell is opened when
+// ANY un-muted body of the group opens it; a body that accepts a cell the group opens takes the
+// interaction and is MUTED (mute = skip of that cell) until the walk leaves the subtree.  The group
+// visits the union of its bodies' cells (probe bh_emul_group_stats: 1.06x the visits of one body for
+// G = 2, 1.14x for G = 4 on the bench cloud).  G = 1 is the plain per-lane walk (no mute logic).
+//
+// One body's share of a visit: 3 FADD2 (packed f32x2 arithmetic of sm_100 on (x, y): the (hi,lo)-split
+// difference of both coordinates), 2 FFMA (d^2); then, packed over PAIRS of bodies (the cell's scalars are
+// broadcast operands): the test t = theta^2 d^2 - s^2, and — after one MUFU.RSQ per body — one Newton step
+// written ic = inv*(d2*inv^2 - 3) (= -2 x the refined 1/sqrt; the factor (-2)^3 is divided out exactly at
+// the end) and m*ic^3; then per body the guard-band compare, ISETP + FSETP (un-muted / accepts / opens),
+// five packed predicated instructions of compensated accumulation, two predicated counters, the mute update.
+// A zero-mass cell is "always accepted" (BH.kt:216 prunes it) and the body's own leaf is skipped
+// (BH.kt:219): one predicate each keeps them out of the sums and the counts.  Finished threads idle on
+// the terminal record cell[M] (mass 0, accepted, skip = M), so there is no per-visit exit test.
+template <int G>
+struct BhMultiResult {
+    double ax[G], ay[G];
+    int interactions[G], opened[G];
+    int retests;
+};
+
+// one 256-bit load of a whole 32-byte cell record (sm_100: LDG.E.256): one L1 wavefront per
+// distinct line instead of two
+__device__ __forceinline__ void bh_load_cell(const BhCell* __restrict__ c, float4* a, float4* b) {
+    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(a->x), "=f"(a->y), "=f"(a->z), "=f"(a->w), "=f"(b->x), "=f"(b->y), "=f"(b->z), "=f"(b->w)
+                 : "l"(c));
+}
+// MUFU.RSQ without the denormal fix-up sequence (d2 >= soft2 is never subnormal)
+__device__ __forceinline__ float bh_mufu_rsq(float v) {
+    float r;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
+    return r;
+}
+
+// How a body's force terms are summed.
+//   BH_ACC_FOLD  FP32 partial sums, folded into f64 every BH_WALK_CHUNK iterations of the loop.  With one
+//                body per thread an iteration is one of the body's own visits, so the result depends on the
+//                body's own walk only; with G > 1 the fold timing follows the GROUP's iterations, i.e. a
+//                body's rounding would depend on its group-mates.
+//   BH_ACC_F64   every term (an FP32 product) is converted and added to an f64 sum right away: no partial
+//                sums, no timing — the result depends on nothing but the body's own sequence of
+//                interactions, however its group-mates are chosen, hence across any multi-GPU partition
+//                of the targets (the bit-identity tests).  5 more issue slots per visit.
+#define BH_ACC_FOLD 0
+#define BH_ACC_F64 1
+
+// Last part of one body's share of a visit: decisions, accumulation, counters, next position.
+// operands  %0 ax  %1 ay  %2 interactions  %3 opened  %4 mute  %5 pnext  |  %6 tt  %7 wg  %8 m  %9 dx
+// %10 dy  %11 skip  %12 p  %13 p+1  %14 own leaf.   Pa accepts, Po opens (while un-muted only), Pc = Pa and
+// mass != 0 and not the own leaf (BH.kt:216,219): the interaction proper.  ax/ay are FP32 or f64.
+#define BH_MULTI_ACC_FOLD_ASM                                                                    \
+        "@Pc fma.rn.f32 %0, %7, %9, %0;\n\t"                                                    \
+        "@Pc fma.rn.f32 %1, %7, %10, %1;\n\t"
+#define BH_MULTI_ACC_F64_ASM   /* FP64 adds are not predicated by ptxas (it would add selects): a masked weight */ \
+        "selp.f32 tx, %7, 0f00000000, Pc;\n\t"           /* makes the term +-0, and x + 0 = x exactly        */ \
+        "mul.f32 ty, tx, %10;\n\t"                                                              \
+        "mul.f32 tx, tx, %9;\n\t"                                                               \
+        "cvt.f64.f32 dx8, tx;\n\t"                                                              \
+        "cvt.f64.f32 dy8, ty;\n\t"                                                              \
+        "add.rn.f64 %0, %0, dx8;\n\t"                                                           \
+        "add.rn.f64 %1, %1, dy8;\n\t"
+#define BH_MULTI_TAIL(J, PRED_ASM, ACC_ASM, ACC_C, MOVE_ASM)                                    \
+    asm("{\n\t"                                                                                 \
+        ".reg .pred Pu, Pa, Po, Pc;\n\t"                                                        \
+        ".reg .f32 tx, ty;\n\t"                                                                 \
+        ".reg .f64 dx8, dy8;\n\t"                                                               \
+        PRED_ASM                                                                                \
+        "setp.neu.and.f32 Pc, %8, 0f00000000, Pa;\n\t"    /* mass != 0 (BH.kt:216)            */ \
+        "setp.ne.and.s32 Pc, %12, %14, Pc;\n\t"           /* not the body's own leaf (:219)   */ \
+        ACC_ASM                                                                                 \
+        "@Pc add.s32 %2, %2, 1;\n\t"                                                            \
+        "@Po add.s32 %3, %3, 1;\n\t"                                                            \
+        MOVE_ASM                                                                                \
         "}"                                                                                     \
-        : "+f"(fx), "+f"(fy), "+r"(ni), "+r"(no), "+r"(p), "+r"(mute)                           \
-        : "f"(tt), "r"(self), "f"(d2), "f"(a.z), "f"(dx), "f"(dy), "r"(__float_as_int(b.z)),    \
-          "r"(gshift), "r"(gmask))
+        : ACC_C(sx[J]), ACC_C(sy[J]), "+r"(ni[J]), "+r"(no[J]), "+r"(mute[J]), "+r"(pnext)      \
+        : "f"(tt[J]), "f"(wg[J]), "f"(c0.z), "f"(dx[J]), "f"(dy[J]), "r"(skip), "r"(p), "r"(p1), "r"(self[J]))
+#define BH_ACC_C_F32 "+f"
+#define BH_ACC_C_F64 "+d"
+// G > 1: the mute logic; the group opens the cell (pnext = p + 1) when any of its bodies does
+#define BH_PRED_GROUP                                                                           \
+        "setp.ge.s32 Pu, %12, %4;\n\t"                    /* un-muted                         */ \
+        "setp.gt.and.f32 Pa|Po, %6, 0f00000000, Pu;\n\t"  /* accepts | opens                  */
+#define BH_MOVE_GROUP                                                                           \
+        "@Pa mov.s32 %4, %11;\n\t"                        /* muted until the walk leaves it   */ \
+        "@Po mov.s32 %5, %13;\n\t"
+// G == 1: the plain per-lane walk (accept -> skip, open -> p + 1)
+#define BH_PRED_SINGLE "setp.gt.f32 Pa|Po, %6, 0f00000000;\n\t"
+#define BH_MOVE_SINGLE "@Po mov.s32 %5, %13;\n\t"
+
+#ifndef BH_WALK_NEWTON
+#define BH_WALK_NEWTON 1      // one Newton step on MUFU.RSQ
+#endif
+// m * (refined 1/sqrt(d2))^3 up to the exact factor BH_WALK_WSCALE, for one body and for a pair of bodies
+// (packed f32x2 instructions of sm_100: the two bodies of a pair share every instruction but the MUFU)
 #if BH_WALK_NEWTON
-#define BH_LANEGROUP_NEWTON_ASM                                                                 \
-    "mul.f32 t2, inv, inv;\n\t"                                                                 \
-    "fma.rn.f32 t1, %8, t2, 0fC0400000;\n\t"                                                    \
-    "mul.f32 inv, inv, t1;\n\t"
+#define BH_WALK_WSCALE (-0.125)   // ic = inv*(d2*inv^2 - 3) = -2 x the refined 1/sqrt: (-2)^3 is divided out at the end
+__device__ __forceinline__ float bh_weight1(float d2, float m) {
+    const float inv = bh_mufu_rsq(d2);
+    const float ic = inv * fmaf(d2, inv * inv, -3.0f);
+    return (m * ic) * (ic * ic);
+}
+__device__ __forceinline__ float2 bh_weight2(float2 d2, float m) {
+    const float2 inv = make_float2(bh_mufu_rsq(d2.x), bh_mufu_rsq(d2.y));
+    const float2 ic = __fmul2_rn(inv, __ffma2_rn(d2, __fmul2_rn(inv, inv), make_float2(-3.0f, -3.0f)));
+    return __fmul2_rn(__fmul2_rn(make_float2(m, m), ic), __fmul2_rn(ic, ic));
+}
 #else
-#define BH_LANEGROUP_NEWTON_ASM ""
+#define BH_WALK_WSCALE 1.0
+__device__ __forceinline__ float bh_weight1(float d2, float m) {
+    const float inv = bh_mufu_rsq(d2);
+    return (m * inv) * (inv * inv);
+}
+__device__ __forceinline__ float2 bh_weight2(float2 d2, float m) {
+    const float2 inv = make_float2(bh_mufu_rsq(d2.x), bh_mufu_rsq(d2.y));
+    return __fmul2_rn(__fmul2_rn(make_float2(m, m), inv), __fmul2_rn(inv, inv));
+}
 #endif
 
-#if defined(__CUDACC__)
-// `group_active`: some lane of this lane's group has a target; `active`: this lane has one.
-template <int LG>
-__device__ __forceinline__ BhWalkResult bh_walk_lanegroup(const BhTreeView& t, const BhWalkParams& w, double x, double y,
-                                                          int self, bool active, bool group_active, int zero) {
-    float xh, xl, yh, yl;
-    bh_split(x, &xh, &xl);
-    bh_split(y, &yh, &yl);
-    BH_OPAQUE_F(xh); BH_OPAQUE_F(xl); BH_OPAQUE_F(yh); BH_OPAQUE_F(yl);
-    BhWalkResult r; r.ax = 0.0; r.ay = 0.0; r.interactions = 0; r.opened = 0; r.retests = 0;
-    const float th2 = w.th2f, soft2 = w.soft2f;
-    const BhCell* __restrict__ cells = t.cell + zero;      // `zero`: see bh_walk_body
-    const int M = t.M;
-    const int gshift = (threadIdx.x & 31) & ~(LG - 1);
-    const int gmask = (1 << LG) - 1;
-    int p = group_active ? 0 : M;
-    int mute = active ? 0 : 0x7fffffff;                     // surplus lanes stay muted for ever
-    int ni = 0, no = 0;
-    while (__any_sync(0xffffffffu, p < M)) {
-        float fx = 0.f, fy = 0.f;
+template <int ACC> struct BhAccT { typedef float type; };
+template <> struct BhAccT<BH_ACC_F64> { typedef double type; };
+
+// x[j], y[j] for j < nactive are the bodies of this thread (Morton-consecutive); every thread of the warp
+// must call (the loop contains full-warp votes).  `zero`: see below.
+template <int G, int ACC>
+__device__ __forceinline__ void bh_walk_multi(const BhTreeView& t, const BhWalkParams& w, const double* x, const double* y,
+                                              const int* self, int nactive, int zero, BhMultiResult<G>* out) {
+    typedef typename BhAccT<ACC>::type acc_t;
+    float2 nh[G], nl[G];                  // -(hi parts), -(lo parts) of the bodies' (x, y)
+    acc_t sx[G], sy[G];                   // BH_ACC_FOLD: FP32 partial sums of the chunk; BH_ACC_F64: the f64 sums
+    double fx[G], fy[G];                  // BH_ACC_FOLD: the f64 sums
+    int ni[G], no[G], mute[G];
 #pragma unroll
-        for (int k = 0; k < BH_WALK_CHUNK; ++k) {
-            float4 a, b;
-            bh_load_cell(cells + p, &a, &b);
-            const float dx = (a.x - xh) + (b.x - xl);
-            const float dy = (a.y - yh) + (b.y - yl);
-            const float d2 = fmaf(dx, dx, fmaf(dy, dy, soft2));
-            float tt = fmaf(d2, th2, -a.w);
-            if (fabsf(tt) <= b.w) {   // borderline: the reference's f64 test decides
-                tt = bh_retest_cell(t.cd, t.sk, p, x, y, w.soft2, w.theta2, w.half) ? 1.0f : -1.0f;
-                r.retests += (p >= mute);
-            }
-            BH_LANEGROUP_VISIT_ASM();
-        }
-        r.ax += (double)fx; r.ay += (double)fy;
+    for (int j = 0; j < G; ++j) {
+        float xh, xl, yh, yl;
+        bh_split(x[j], &xh, &xl);
+        bh_split(y[j], &yh, &yl);
+        nh[j] = make_float2(-xh, -yh);
+        nl[j] = make_float2(-xl, -yl);
+        sx[j] = 0; sy[j] = 0; fx[j] = 0.0; fy[j] = 0.0; ni[j] = 0; no[j] = 0;
+        mute[j] = (j < nactive) ? 0 : 0x7fffffff;     // surplus slots stay muted for ever
     }
-    r.interactions = ni; r.opened = no;
-#if BH_WALK_NEWTON
-    r.ax *= -0.125; r.ay *= -0.125;
-#endif
-    return r;
+    int retests = 0;
+    const float th2 = w.th2f, soft2 = w.soft2f;
+    // `zero` is a 0 the compiler cannot see through (loaded from memory): it keeps the base pointer in registers,
+    // so that the record address is ONE IMAD.WIDE (p * 32 + base) instead of a constant-bank reload per visit
+    const BhCell* __restrict__ cells;
+    asm volatile("mad.wide.s32 %0, %1, 32, %2;" : "=l"(cells) : "r"(zero), "l"(t.cell));
+    const int M = t.M;
+    int p = nactive > 0 ? 0 : M;
+    while (__any_sync(0xffffffffu, p < M)) {
+#pragma unroll
+        for (int k = 0; k < BH_WALK_CHUNK / (G > 2 ? 2 : 1); ++k) {
+            float4 c0, c1;
+            bh_load_cell(cells + p, &c0, &c1);
+            const int skip = __float_as_int(c1.z);
+            const int p1 = p + 1;
+            int pnext = skip;
+            const float2 ch = make_float2(c0.x, c0.y), cl = make_float2(c1.x, c1.y);
+            float dx[G], dy[G], d2[G], tt[G], wg[G];
+            bool border = false;
+#pragma unroll
+            for (int j = 0; j < G; ++j) {
+                const float2 d = __fadd2_rn(__fadd2_rn(ch, nh[j]), __fadd2_rn(cl, nl[j]));   // (hi - hi) + (lo - lo), both axes
+                dx[j] = d.x; dy[j] = d.y;
+                d2[j] = fmaf(d.x, d.x, fmaf(d.y, d.y, soft2));
+            }
+            if constexpr (G == 1) {
+                tt[0] = fmaf(d2[0], th2, -c0.w);
+                wg[0] = bh_weight1(d2[0], c0.z);
+                border = fabsf(tt[0]) <= c1.w;
+            } else {
+#pragma unroll
+                for (int j = 0; j + 1 < G; j += 2) {      // two bodies per packed instruction
+                    const float2 d2p = make_float2(d2[j], d2[j + 1]);
+                    const float2 tp = __ffma2_rn(d2p, make_float2(th2, th2), make_float2(-c0.w, -c0.w));
+                    const float2 wp = bh_weight2(d2p, c0.z);
+                    tt[j] = tp.x; tt[j + 1] = tp.y; wg[j] = wp.x; wg[j + 1] = wp.y;
+                    border |= fminf(fabsf(tp.x), fabsf(tp.y)) <= c1.w;
+                }
+            }
+            if (border) {   // some body is inside the guard band: the reference's f64 test decides (cold)
+#pragma unroll
+                for (int j = 0; j < G; ++j)
+                    if (fabsf(tt[j]) <= c1.w) {
+                        tt[j] = bh_retest_cell(t.cd, t.sk, p, x[j], y[j], w.soft2, w.theta2, w.half) ? 1.0f : -1.0f;
+                        retests += (p >= mute[j]);
+                    }
+            }
+#pragma unroll
+            for (int j = 0; j < G; ++j) {
+                if constexpr (G == 1) {
+                    if constexpr (ACC == BH_ACC_F64) { BH_MULTI_TAIL(j, BH_PRED_SINGLE, BH_MULTI_ACC_F64_ASM, BH_ACC_C_F64, BH_MOVE_SINGLE); }
+                    else { BH_MULTI_TAIL(j, BH_PRED_SINGLE, BH_MULTI_ACC_FOLD_ASM, BH_ACC_C_F32, BH_MOVE_SINGLE); }
+                } else {
+                    if constexpr (ACC == BH_ACC_F64) { BH_MULTI_TAIL(j, BH_PRED_GROUP, BH_MULTI_ACC_F64_ASM, BH_ACC_C_F64, BH_MOVE_GROUP); }
+                    else { BH_MULTI_TAIL(j, BH_PRED_GROUP, BH_MULTI_ACC_FOLD_ASM, BH_ACC_C_F32, BH_MOVE_GROUP); }
+                }
+            }
+            p = pnext;
+        }
+        if constexpr (ACC == BH_ACC_FOLD) {
+#pragma unroll
+            for (int j = 0; j < G; ++j) { fx[j] += (double)sx[j]; fy[j] += (double)sy[j]; sx[j] = 0; sy[j] = 0; }
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < G; ++j) {
+        out->ax[j] = (ACC == BH_ACC_FOLD ? fx[j] : (double)sx[j]) * BH_WALK_WSCALE;     // the scale is a power of two: exact
+        out->ay[j] = (ACC == BH_ACC_FOLD ? fy[j] : (double)sy[j]) * BH_WALK_WSCALE;
+        out->interactions[j] = ni[j];
+        out->opened[j] = no[j];
+    }
+    out->retests = retests;
 }
 #endif
 
@@ -787,165 +829,6 @@ BH_HD double bh_walk_potential(const BhTreeView& t, const BhWalkParams& w, doubl
         phi += (double)f;
     }
     return phi;
-}
-
-// ---- group walk: G bodies per thread, one shared preorder position ---------------------------
-// The per-lane walk above is bound by the L1 data stage: every lane of a warp is at a different
-// cell, so one warp-wide load touches ~15 distinct 32 B sectors.  Here a THREAD walks for G
-// Morton-consecutive bodies at once: the cell is loaded once and tested against the G bodies
-// (G independent dependency chains: instruction-level parallelism instead of occupancy).  The
-// per-body decisions stay the reference's: a cell is opened when ANY un-muted body of the group
-// opens it; a body that accepts a cell the group opens takes the interaction and is muted
-// (`mute` = skip of that cell) until the walk leaves the subtree.  The group visits the union of
-// its bodies' cells, ~1.14x the visits of one body for G = 4 (probe: bh_emul_group_stats), and a
-// warp-wide load now serves 32*G body visits.
-template <int G>
-struct BhGroupResult {
-    double ax[G], ay[G];
-    int interactions[G], opened[G];
-    int retests;
-};
-
-// second half of one body's share of a group visit: operands  %0 fx  %1 fy  %2 interactions
-// %3 opened  %4 mute  %5 gmin  |  %6 t  %7 p  %8 self  %9 d2  %10 m  %11 dx  %12 dy  %13 skip
-// gmin = NaN-ignoring minimum of the un-muted bodies' t: the group opens the cell iff gmin < 0.
-#define BH_GROUP_BODY_ASM(ZM)                                                                   \
-    asm volatile(                                                                               \
-        "{\n\t"                                                                                 \
-        ".reg .pred Pu, P0, Pw, P1;\n\t"                                                        \
-        ".reg .f32 te, inv, t1, t2, wg;\n\t"                                                    \
-        "setp.ge.s32 Pu, %7, %4;\n\t"                  /* un-muted                         */   \
-        "selp.f32 te, %6, 0f7FC00000, Pu;\n\t"         /* muted: neither accepts nor opens */   \
-        "setp.gt.f32 P0, te, 0f00000000;\n\t"          /* accepts                          */   \
-        "setp.lt.f32 Pw, te, 0f00000000;\n\t"          /* wants the cell opened            */   \
-        "min.f32 %5, %5, te;\n\t"                                                               \
-        "setp.ne.and.s32 P1, %7, %8, P0;\n\t"          /* ... and not the body's own leaf  */   \
-        ZM                                                                                      \
-        "rsqrt.approx.ftz.f32 inv, %9;\n\t"                                                     \
-        BH_GROUP_NEWTON_ASM                                                                     \
-        "mul.f32 wg, %10, inv;\n\t"                                                             \
-        "mul.f32 wg, wg, inv;\n\t"                                                              \
-        "mul.f32 wg, wg, inv;\n\t"                                                              \
-        "@P1 fma.rn.f32 %0, wg, %11, %0;\n\t"                                                   \
-        "@P1 fma.rn.f32 %1, wg, %12, %1;\n\t"                                                   \
-        "@P1 add.s32 %2, %2, 1;\n\t"                                                            \
-        "@Pw add.s32 %3, %3, 1;\n\t"                                                            \
-        "@P0 mov.s32 %4, %13;\n\t"                     /* muted until the walk leaves the cell */ \
-        "}"                                                                                     \
-        : "+f"(fx[j]), "+f"(fy[j]), "+r"(ni[j]), "+r"(no[j]), "+r"(mute[j]), "+f"(gmin)         \
-        : "f"(tt[j]), "r"(p), "r"(slf[j]), "f"(d2[j]), "f"(a.z), "f"(dx[j]), "f"(dy[j]), "r"(skip))
-#if BH_WALK_NEWTON
-#define BH_GROUP_NEWTON_ASM                                                                     \
-    "mul.f32 t2, inv, inv;\n\t"                                                                 \
-    "fma.rn.f32 t1, %9, t2, 0fC0400000;\n\t"                                                    \
-    "mul.f32 inv, inv, t1;\n\t"
-#else
-#define BH_GROUP_NEWTON_ASM ""
-#endif
-
-template <int G, bool ZERO_MASS>
-BH_HD void bh_walk_group(const BhTreeView& t, const BhWalkParams& w, const double* x, const double* y, const int* self,
-                         int nactive, int zero, BhGroupResult<G>* out) {
-    float xh[G], xl[G], yh[G], yl[G], fx[G], fy[G];
-    double sx[G], sy[G];
-    int ni[G], no[G], mute[G], slf[G];
-#pragma unroll
-    for (int j = 0; j < G; ++j) {
-        bh_split(x[j], &xh[j], &xl[j]);
-        bh_split(y[j], &yh[j], &yl[j]);
-        BH_OPAQUE_F(xh[j]); BH_OPAQUE_F(xl[j]); BH_OPAQUE_F(yh[j]); BH_OPAQUE_F(yl[j]);
-        sx[j] = 0.0; sy[j] = 0.0; ni[j] = 0; no[j] = 0;
-        mute[j] = (j < nactive) ? 0 : 0x7fffffff;     // surplus slots stay muted for ever
-        slf[j] = self[j];
-    }
-    int retests = 0;
-    const float th2 = w.th2f, soft2 = w.soft2f;
-    const BhCell* __restrict__ cells = t.cell + zero;   // `zero`: see bh_walk_body
-    const int M = t.M;
-    int p = nactive > 0 ? 0 : M;
-    int gv = 0, iters = 0;                              // real group visits / all iterations
-#if defined(__CUDA_ARCH__)
-    while (__any_sync(0xffffffffu, p < M)) {
-#pragma unroll
-        for (int j = 0; j < G; ++j) { fx[j] = 0.f; fy[j] = 0.f; }
-#pragma unroll 2
-        for (int k = 0; k < BH_WALK_CHUNK; ++k) {
-            float4 a, b;
-            bh_load_cell(cells + p, &a, &b);
-            const int skip = __float_as_int(b.z);
-            float dx[G], dy[G], d2[G], tt[G];
-            bool border = false;
-#pragma unroll
-            for (int j = 0; j < G; ++j) {
-                dx[j] = (a.x - xh[j]) + (b.x - xl[j]);
-                dy[j] = (a.y - yh[j]) + (b.y - yl[j]);
-                d2[j] = fmaf(dx[j], dx[j], fmaf(dy[j], dy[j], soft2));
-                tt[j] = fmaf(d2[j], th2, -a.w);
-                border |= fabsf(tt[j]) <= b.w;
-            }
-            if (border) {   // some body is inside the guard band: the reference's f64 test decides
-#pragma unroll
-                for (int j = 0; j < G; ++j)
-                    if (fabsf(tt[j]) <= b.w) {
-                        tt[j] = bh_retest_cell(t.cd, t.sk, p, x[j], y[j], w.soft2, w.theta2, w.half) ? 1.0f : -1.0f;
-                        retests += (p >= mute[j]);
-                    }
-            }
-            float gmin = 1.0f;
-#pragma unroll
-            for (int j = 0; j < G; ++j) {
-                if (ZERO_MASS) { BH_GROUP_BODY_ASM("setp.neu.and.f32 P1, %10, 0f00000000, P1;\n\t"); }
-                else { BH_GROUP_BODY_ASM(""); }
-            }
-            gv += (p < M);
-            p = (gmin < 0.0f) ? p + 1 : skip;
-        }
-        iters += BH_WALK_CHUNK;
-#pragma unroll
-        for (int j = 0; j < G; ++j) { sx[j] += (double)fx[j]; sy[j] += (double)fy[j]; }
-    }
-#else
-    while (p < M) {
-        const BhCell& c = cells[p];
-        bool gopen = false;
-        for (int j = 0; j < G; ++j) {
-            const float dx = (c.xh - xh[j]) + (c.xl - xl[j]);
-            const float dy = (c.yh - yh[j]) + (c.yl - yl[j]);
-            const float d2 = fmaf(dx, dx, fmaf(dy, dy, soft2));
-            const float tt = fmaf(d2, th2, -c.s2);
-            const bool unmuted = p >= mute[j];
-            bool acc = tt > 0.0f;
-            if (fabsf(tt) <= c.band) {
-                acc = bh_retest_cell(t.cd, t.sk, p, x[j], y[j], w.soft2, w.theta2, w.half);
-                retests += unmuted;
-            }
-            if (!unmuted) continue;
-            if (!acc) { gopen = true; no[j]++; continue; }
-            const float ic = BH_RSQRTF(d2);
-            if (p != slf[j] && (!ZERO_MASS || c.m != 0.0f)) {
-                const float wg = c.m * ic * ic * ic;
-                sx[j] += (double)(wg * dx); sy[j] += (double)(wg * dy);
-                ni[j]++;
-            }
-            mute[j] = c.skip;
-        }
-        ++gv; ++iters;
-        p = gopen ? p + 1 : c.skip;
-    }
-    (void)fx; (void)fy;
-#endif
-#pragma unroll
-    for (int j = 0; j < G; ++j) {
-#if defined(__CUDA_ARCH__) && BH_WALK_NEWTON
-        out->ax[j] = sx[j] * -0.125; out->ay[j] = sy[j] * -0.125;
-#else
-        out->ax[j] = sx[j]; out->ay[j] = sy[j];
-#endif
-        // idle iterations on the terminal record were counted as interactions unless ZERO_MASS
-        out->interactions[j] = (j < nactive) ? ni[j] - (ZERO_MASS ? 0 : (iters - gv)) : 0;
-        out->opened[j] = no[j];
-    }
-    out->retests = retests;
 }
 
 #endif  // BH_CORE_H

@@ -1,7 +1,7 @@
 // bh_engine.cu — B200 (sm_100a) Barnes–Hut physics-step engine behind include/bh_engine.h.
 //
 // One PhysicsEngine.step() of the reference (BarnesHutAlg.kt:405-439) becomes, per force
-// evaluation:  k_keygen -> onesweep radix sort -> k_count_scan -> k_emit -> k_climb -> k_walk,
+// evaluation:  k_keygen -> onesweep radix sort -> k_count_scan -> k_emit -> k_climb_block/top -> k_walk,
 // then the f64 kick/drift kernels and the merge rule.  The tree is the reference's own quadtree
 // (same cells, same f64 centres of mass, same per-body accept/open decisions) stored as a
 // flattened DFS-preorder array with skip links; see bh_core.h, bh_kernels.cuh and DESIGN.md.
@@ -51,7 +51,7 @@ inline int grid_for(int64_t n, int block) { return (int)((n + block - 1) / block
 
 constexpr int PAD = 64;            // slack behind every body array (in-place all-gather of padded slices)
 constexpr int MAX_WORLD = 64;
-enum HostFlag { HF_ZERO_MASS = 0, HF_N_DEAD = 1, HF_N_CAND = 2, HF_N_ROOTS = 3, HF_COUNT = 4 };
+enum HostFlag { HF_SPARE = 0, HF_N_DEAD = 1, HF_N_CAND = 2, HF_N_ROOTS = 3, HF_COUNT = 4 };
 
 }  // namespace
 
@@ -86,7 +86,6 @@ struct bh_engine {
     bool jitter_active = false;      // the last build replayed jitter clusters
     int *cntI = nullptr, *cntO = nullptr;
     bool perm_identity = true, origin_identity = true;
-    bool any_zero_mass = false;      // some body has m == 0 (zero-mass cells are pruned, BH.kt:216)
     int* dflags = nullptr;           // device flags / small counters (HostFlag)
     int* hflags = nullptr;           // pinned mirror
 
@@ -387,6 +386,11 @@ struct bh_engine {
         n_in = sc_host->n_in; n_internal = sc_host->n_internal; M = n_in + n_internal;
         ctr.n_in_tree = n_in; ctr.n_out_of_box = n - n_in; ctr.n_internal = n_internal; ctr.n_cells = M;
         ctr.n_jitter_bodies = sc_host->n_jitter; ctr.max_depth = sc_host->max_depth; ctr.key_levels = root.levels;
+        if (!let.local_build) {      // (a local build of the domain mode sees this rank's bodies only)
+            const bool any = sc_host->bb[0] != 0;
+            ctr.bbox_max_x = any ? bh_ord_unkey(sc_host->bb[0]) : nan(""); ctr.bbox_min_x = any ? bh_ord_unkey(~sc_host->bb[1]) : nan("");
+            ctr.bbox_max_y = any ? bh_ord_unkey(sc_host->bb[2]) : nan(""); ctr.bbox_min_y = any ? bh_ord_unkey(~sc_host->bb[3]) : nan("");
+        }
         if (let.local_build && (int64_t)M + 1 > cell_cap) {
             // Domain mode: the peers map this rank's cell arrays, so a local build must never re-allocate them.
             // (A local tree has no more cells than the global tree the arrays were sized for; this can only
@@ -415,7 +419,7 @@ struct bh_engine {
             const BhTreeView t = view();
             k_emit<<<grid_for(n_in, 256), 256, 0, st>>>(t, root.levels);
             BH_RC(wait_inputs());   // bh_step_io: the masses may still be in flight
-            if (climb_block) {
+            {
                 if (n_in > climb_roots_cap) {
                     dev_free(climb_roots);
                     climb_roots_cap = std::max<int64_t>(n_in + n_in / 8, 1024);
@@ -426,10 +430,8 @@ struct bh_engine {
                 k_climb_block<<<grid_for(n_in, CLIMB_B), CLIMB_B, 0, st>>>(t, root, x, y, m, jitter_active ? jflag : nullptr, leafpos,
                                                                              climb_roots, n_roots);
                 k_climb_top<<<std::min(grid_for(n_in, 128 * 8), num_sms * 8), 128, 0, st>>>(t, root, climb_roots, n_roots);
-                ctr.kernel_launches += 1;
-            } else
-                k_climb<<<grid_for(n_in, 256), 256, 0, st>>>(t, root, x, y, m, jitter_active ? jflag : nullptr, leafpos);
-            ctr.kernel_launches += 2;
+                ctr.kernel_launches += 3;
+            }
         }
         if (timed) BH_TRY(cudaEventRecord(ev[slot + 1], st));
         BH_TRY(cudaGetLastError());
@@ -438,9 +440,10 @@ struct bh_engine {
     }
     int64_t ctr_rehomes = 0, ctr_reused = 0;
     int io_steps_left = 0;
-    bool climb_block = true;        // BH_CLIMB_BLOCK=0: per-thread global climb (k_climb)
-    bool walk_lanegroup = false;     // BH_WALK_LANEGROUP=1: 4 adjacent lanes share one position (bh_walk_lanegroup)
-    int walk_group_min_waves = 0;   // BH_WALK_GROUP_MIN_WAVES > 0: group walk from this many waves of 128-thread blocks per SM
+    int walk_g = 0;                 // bodies per thread of the walk; 0 = automatic (BH_WALK_G=1|2 pins it)
+    bool walk_affine = true;        // BH_WALK_AFFINE=0: every chunk from the global queue (no SM affinity)
+    unsigned int* walk_queue = nullptr;   // work counters of the persistent walk kernel
+    int walk_acc = -1;              // BH_WALK_ACC=1: f64 summation (BH_ACC_F64) also for one body per lane
 
     int sort_pairs(int nn, int key_bits) {
         // the sort zeroes nothing itself here: build() already cleared the scratch region
@@ -473,21 +476,31 @@ struct bh_engine {
         BH_TRY(cudaEventRecord(ev[slot + 2], st));
         if (count > 0) {
             const BhWalkParams w = bh_walk_params(par.theta, par.soft2, par.root_half);
-            // experimental 4-bodies-per-thread walk (see bh_walk_group): same speed as the per-lane
-            // walk on B200 at 1M bodies (issue-bound instead of L1-data-stage-bound), so off by default
-            if (walk_group_min_waves > 0 && count >= (int64_t)num_sms * 128 * WALK_G * walk_group_min_waves) {
-                const int g = grid_for((count + WALK_G - 1) / WALK_G, 128);
-                if (any_zero_mass)
-                    k_walk_group<true><<<g, 128, 0, st>>>(tv, w, (int)first, (int)count, x, y, m, leafpos, par.G, ax, ay, cntI, cntO, sc(), tot);
-                else
-                    k_walk_group<false><<<g, 128, 0, st>>>(tv, w, (int)first, (int)count, x, y, m, leafpos, par.G, ax, ay, cntI, cntO, sc(), tot);
-            } else if (walk_lanegroup) {
-                const int g = grid_for(count, 128);
-                k_walk_lanegroup<<<g, 128, 0, st>>>(tv, w, (int)first, (int)count, x, y, m, leafpos, par.G, ax, ay, cntI, cntO, sc(), tot);
-            } else {
-                const int g = grid_for(count, 128);
-                k_walk<<<g, 128, 0, st>>>(tv, w, (int)first, (int)count, x, y, m, leafpos, par.G, ax, ay, cntI, cntO, sc(), tot);
-            }
+            // bodies per thread (bh_walk_multi): the widest group that still gives every SM >= 2 full waves of
+            // 128-thread blocks; few targets -> one body per lane.  BH_WALK_G pins it (measurements).
+            // bodies per thread: pairs (sharing every record load) when there are enough targets to fill the machine
+            // with half the threads, else one body per lane.  Pairs add every term to an f64 sum at once (BH_ACC_F64),
+            // which keeps a body's result independent of its partner; a single body folds FP32 partial sums every
+            // BH_WALK_CHUNK of its own visits (BH_ACC_FOLD).  BH_WALK_G / BH_WALK_ACC pin the choice (tests).
+            int g = walk_g;
+            if (g == 0) g = count >= (int64_t)num_sms * 128 * 16 ? 2 : 1;
+            g = g >= 2 ? 2 : 1;
+            const bool f64acc = walk_acc == BH_ACC_F64 || (walk_acc < 0 && g > 1) || g > 1;
+            // persistent SM-affine schedule (see k_walk): one range of chunks per SM, stealing between ranges
+            BhWalkQueue q;
+            q.next = walk_queue;
+            q.n_ranges = num_sms;
+            q.chunks = (int)((count + 32 * g - 1) / (32 * g));
+            q.per = (q.chunks + q.n_ranges - 1) / q.n_ranges;
+            if (!walk_affine) { q.n_ranges = 1; q.per = q.chunks; }     // one queue: no SM affinity
+            BH_TRY(cudaMemsetAsync(walk_queue, 0, (size_t)q.n_ranges * sizeof(unsigned int), st));
+#define BH_LAUNCH_WALK(GG, AA, MINB)                                                                                        \
+    k_walk<GG, AA, MINB><<<(int)std::min<int64_t>((q.chunks + 3) / 4, (int64_t)num_sms * MINB), 128, 0, st>>>(              \
+        tv, w, (int)first, (int)count, x, y, m, leafpos, par.G, ax, ay, cntI, cntO, sc(), tot, q)
+            if (g == 2) BH_LAUNCH_WALK(2, BH_ACC_F64, 7);
+            else if (f64acc) BH_LAUNCH_WALK(1, BH_ACC_F64, 9);
+            else BH_LAUNCH_WALK(1, BH_ACC_FOLD, 9);
+#undef BH_LAUNCH_WALK
             ctr.kernel_launches += 1;
         }
         BH_TRY(cudaEventRecord(ev[slot + 3], st));
@@ -723,9 +736,9 @@ int bh_create(const bh_config* cfg, bh_engine** out) {
     e->device = e->cfg.device;
     e->rehome_interval = e->cfg.rehome_interval > 0 ? e->cfg.rehome_interval : 8;
     if (const char* s = getenv("BH_REHOME_INTERVAL")) { const int v = atoi(s); if (v > 0) e->rehome_interval = v; }
-    if (const char* s = getenv("BH_WALK_GROUP_MIN_WAVES")) e->walk_group_min_waves = atoi(s);
-    if (const char* s = getenv("BH_CLIMB_BLOCK")) e->climb_block = atoi(s) != 0;
-    if (const char* s = getenv("BH_WALK_LANEGROUP")) e->walk_lanegroup = atoi(s) != 0;
+    if (const char* s = getenv("BH_WALK_G")) e->walk_g = atoi(s);
+    if (const char* s = getenv("BH_WALK_ACC")) e->walk_acc = atoi(s);
+    if (const char* s = getenv("BH_WALK_AFFINE")) e->walk_affine = atoi(s) != 0;
     cudaError_t ce = cudaSetDevice(e->device);
     if (ce == cudaSuccess) ce = cudaStreamCreateWithFlags(&e->st, cudaStreamNonBlocking);
     for (auto& sl : e->ring) for (int k = 0; k < 16 && ce == cudaSuccess; ++k) ce = cudaEventCreate(&sl.e[k]);
@@ -737,6 +750,7 @@ int bh_create(const bh_config* cfg, bh_engine** out) {
     if (ce == cudaSuccess) ce = dev_alloc(&e->tot, 1);
     if (ce == cudaSuccess) ce = cudaMemset(e->tot, 0, sizeof(DevTotals));
     if (ce == cudaSuccess) ce = dev_alloc(&e->red, 4);
+    if (ce == cudaSuccess) ce = dev_alloc(&e->walk_queue, 1024);
     if (ce == cudaSuccess) ce = cudaDeviceGetAttribute(&e->num_sms, cudaDevAttrMultiProcessorCount, e->device);
     if (ce != cudaSuccess) {
         g_create_err = std::string("bh_create: CUDA device ") + std::to_string(e->device) + " unavailable: " +
@@ -768,7 +782,7 @@ void bh_destroy(bh_engine* e) {
     e->free_bodies();
     e->free_cells();
     e->let.release();
-    dev_free(e->tot); dev_free(e->red); dev_free(e->dflags); dev_free(e->heavy);
+    dev_free(e->tot); dev_free(e->red); dev_free(e->walk_queue); dev_free(e->dflags); dev_free(e->heavy);
     if (e->sc_host) cudaFreeHost(e->sc_host);
     if (e->tot_host) cudaFreeHost(e->tot_host);
     if (e->hflags) cudaFreeHost(e->hflags);
@@ -826,13 +840,9 @@ int bh_set_bodies(bh_engine* e, int64_t n, const double* x, const double* y, con
         E_TRY(cudaMemsetAsync(e->ax, 0, bytes, e->st));
         E_TRY(cudaMemsetAsync(e->ay, 0, bytes, e->st));
         E_TRY(cudaMemsetAsync(e->dflags, 0, HF_COUNT * sizeof(int), e->st));
-        k_flag_zero_mass<<<grid_for(n, 256), 256, 0, e->st>>>(e->m, (int)n, e->dflags + HF_ZERO_MASS);
-        E_TRY(cudaMemcpyAsync(e->hflags, e->dflags, HF_COUNT * sizeof(int), cudaMemcpyDeviceToHost, e->st));
-        e->ctr.kernel_launches += 2;
     }
     E_TRY(cudaStreamSynchronize(e->st));
     E_TRY(cudaGetLastError());
-    e->any_zero_mass = n > 0 && e->hflags[HF_ZERO_MASS] != 0;
     e->origin_identity = true;
     e->tree_valid = false;
     e->heavies_valid = false;
@@ -1097,13 +1107,9 @@ int bh_step_io(bh_engine* e, int32_t nsteps, int64_t n_in, const double* x_in, c
                 k_gather<double><<<grid_for(n_new, 256), 256, 0, e->copy_st>>>(dev[k], e->io_stage[k], e->perm, (int)n_new);
             }
         }
-        E_TRY(cudaMemsetAsync(e->dflags, 0, sizeof(int), e->copy_st));
-        k_flag_zero_mass<<<grid_for(n_new, 256), 256, 0, e->copy_st>>>(e->m, (int)n_new, e->dflags + HF_ZERO_MASS);
-        E_TRY(cudaMemcpyAsync(e->hflags, e->dflags, sizeof(int), cudaMemcpyDeviceToHost, e->copy_st));
         E_TRY(cudaEventRecord(e->io_ev[0], e->copy_st));
         e->io_wait_in = true;
-        e->any_zero_mass = true;     // unknown until the flag arrives: the steps use the zero-mass-safe walk
-        e->ctr.kernel_launches += 6;
+        e->ctr.kernel_launches += 3;
         e->origin_identity = true;
         e->tree_valid = false; e->heavies_valid = false; e->vel_valid = true; e->acc_valid = false;
     }
@@ -1135,7 +1141,6 @@ int bh_step_io(bh_engine* e, int32_t nsteps, int64_t n_in, const double* x_in, c
     }
     cudaError_t c1 = cudaStreamSynchronize(e->st), c2 = cudaStreamSynchronize(e->copy_st);
     if (rc == BH_OK && (c1 != cudaSuccess || c2 != cudaSuccess)) rc = e->cuda_fail(c1 != cudaSuccess ? c1 : c2, "bh_step_io");
-    if (x_in) e->any_zero_mass = e->hflags[HF_ZERO_MASS] != 0;
     if (n_out) *n_out = e->n;
     return rc;
 }
@@ -1170,9 +1175,14 @@ int bh_direct_sum(bh_engine* e, double* ax, double* ay) {
     double* dax = reinterpret_cast<double*>(e->keys_a);
     double* day = reinterpret_cast<double*>(e->keys_b);
     e->tree_valid = false;
+    E_TRY(cudaEventRecord(e->call_ev[0], e->st));
     k_direct<<<grid_for(e->n, DS_TILE), DS_TILE, 0, e->st>>>(e->x, e->y, e->m, (int)e->n, (float)e->par.soft2, e->par.G, dax, day);
+    E_TRY(cudaEventRecord(e->call_ev[1], e->st));
     e->ctr.kernel_launches += 1;
     E_TRY(cudaGetLastError());
+    E_TRY(cudaEventSynchronize(e->call_ev[1]));
+    float dms = 0.f;
+    if (cudaEventElapsedTime(&dms, e->call_ev[0], e->call_ev[1]) == cudaSuccess) e->ctr.ms_direct = dms;
     E_RC(e->download_user(ax, (const double*)dax, e->dtmp));
     E_RC(e->download_user(ay, (const double*)day, e->dtmp));
     E_TRY(cudaStreamSynchronize(e->st));
@@ -1334,6 +1344,8 @@ int bh_reset_counters(bh_engine* e) {
     e->ctr.n_internal = keep.n_internal; e->ctr.key_levels = keep.key_levels; e->ctr.max_depth = keep.max_depth;
     e->ctr.n_jitter_bodies = keep.n_jitter_bodies;
     e->ctr.ms_step_call = keep.ms_step_call;
+    e->ctr.bbox_min_x = keep.bbox_min_x; e->ctr.bbox_max_x = keep.bbox_max_x; e->ctr.bbox_min_y = keep.bbox_min_y; e->ctr.bbox_max_y = keep.bbox_max_y;
+    e->ctr.ms_direct = keep.ms_direct;
     return BH_OK;
 }
 
@@ -1429,6 +1441,35 @@ int bh_import_slices(bh_engine* e, int32_t field, int64_t n, const double* a, co
     E_TRY(cudaStreamSynchronize(e->st));
     if (field == BH_FIELD_VEL) e->vel_valid = true;
     else { e->tree_valid = false; e->acc_valid = false; }
+    return BH_OK;
+}
+
+int bh_evaluate_slice(bh_engine* e, int64_t cap, double* ax, double* ay, int32_t* user_index, int64_t* n_slice) {
+    if (!e) return BH_E_ARG;
+    E_TRY(cudaSetDevice(e->device));
+    if (e->phase != 0) return e->fail(BH_E_STATE, "bh_evaluate_slice: a step is in progress");
+    e->acc_valid = false;
+    E_RC(e->evaluate_slice(0));
+    E_RC(e->finish());
+    e->add_phase_times(0);
+    int64_t lo, hi;
+    e->my_slice(&lo, &hi);                 // (a re-homing build inside the evaluation may have re-cut the slices)
+    if (n_slice) *n_slice = hi - lo;
+    if (cap < hi - lo) return e->fail(BH_E_ARG, "bh_evaluate_slice: capacity too small");
+    if (hi > lo) {
+        const size_t k = (size_t)(hi - lo);
+        if (ax) E_TRY(cudaMemcpyAsync(ax, e->ax + lo, k * sizeof(double), cudaMemcpyDeviceToHost, e->st));
+        if (ay) E_TRY(cudaMemcpyAsync(ay, e->ay + lo, k * sizeof(double), cudaMemcpyDeviceToHost, e->st));
+        if (user_index) E_TRY(cudaMemcpyAsync(user_index, e->perm + lo, k * sizeof(int32_t), cudaMemcpyDeviceToHost, e->st));
+        E_TRY(cudaStreamSynchronize(e->st));
+    }
+    return BH_OK;
+}
+
+int bh_set_domain_mode(bh_engine* e, int32_t enabled) {
+    if (!e) return BH_E_ARG;
+    if (e->phase != 0) return e->fail(BH_E_STATE, "bh_set_domain_mode: a step is in progress");
+    e->let.enabled = enabled != 0 && e->world > 1 && e->world <= 16 && e->transport == bh_engine::T_NCCL;
     return BH_OK;
 }
 

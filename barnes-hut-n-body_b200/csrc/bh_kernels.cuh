@@ -22,10 +22,29 @@ struct DevScalars {           // zeroed at the start of every build
     int max_depth;
     unsigned long long interactions, opened, retests;   // of the evaluation that follows
     unsigned int scan_ticket;
-    unsigned int pad;         // always 0: the walk adds it to its base pointer (see bh_walk_body)
+    unsigned int pad;         // always 0: the walk adds it to its base pointer (see bh_walk_multi)
     int n_ghost;              // bodies dropped by the jitter replay (ghost leaves)
     int jitter_unsupported;   // a jittered body survived below depth levels+1 (cannot happen for h < 1e-3)
+    // bounding box of all bodies as order-preserving keys (bh_ord_key): max of key(x), max of ~key(x), same for y;
+    // all-zero = no body seen (the scalars are zeroed per build)
+    unsigned long long bb[4];
 };
+// order-preserving map double -> uint64 (and back): a < b  <=>  key(a) < key(b); key is never 0 for a finite value
+__host__ __device__ inline unsigned long long bh_ord_key(double v) {
+    unsigned long long b;
+#if defined(__CUDA_ARCH__)
+    b = (unsigned long long)__double_as_longlong(v);
+#else
+    memcpy(&b, &v, 8);
+#endif
+    return (b & 0x8000000000000000ull) ? ~b : (b | 0x8000000000000000ull);
+}
+inline double bh_ord_unkey(unsigned long long k) {
+    const unsigned long long b = (k & 0x8000000000000000ull) ? (k & 0x7fffffffffffffffull) : ~k;
+    double v;
+    memcpy(&v, &b, 8);
+    return v;
+}
 struct DevTotals {            // zeroed by bh_reset_counters only
     unsigned long long interactions, opened, retests, evaluations;
 };
@@ -76,8 +95,14 @@ __global__ void __launch_bounds__(256) k_keygen(const double* __restrict__ x, co
                                                 DevScalars* __restrict__ sc, int ell = -1, uint32_t c_lo = 0, uint32_t c_hi = 0) {
     // grid-stride: ONE atomic per block for the in-box count (same-address atomics serialise in L2)
     int cnt = 0;
+    unsigned long long bb0 = 0, bb1 = 0, bb2 = 0, bb3 = 0;   // running max of key(x), ~key(x), key(y), ~key(y)
     for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < n; b += gridDim.x * blockDim.x) {
         const double px = x[b], py = y[b];
+        if (px == px && py == py) {                          // bounding box of every body, in the box or not
+            const unsigned long long kx = bh_ord_key(px), ky = bh_ord_key(py);
+            bb0 = kx > bb0 ? kx : bb0; bb1 = ~kx > bb1 ? ~kx : bb1;
+            bb2 = ky > bb2 ? ky : bb2; bb3 = ~ky > bb3 ? ~ky : bb3;
+        }
         bool in = bh_root_contains(root, px, py);
         // closed form on the exact grid when the root box allows it, else the literal descent
         uint64_t key = in ? (grid.exact ? bh_morton_key_grid(grid, root.levels, px, py) : bh_morton_key(root, px, py)) : sentinel;
@@ -90,14 +115,26 @@ __global__ void __launch_bounds__(256) k_keygen(const double* __restrict__ x, co
     }
     if (sc) {
         __shared__ int s_cnt;
-        if (threadIdx.x == 0) s_cnt = 0;
+        __shared__ unsigned long long s_bb[4];
+        if (threadIdx.x == 0) { s_cnt = 0; s_bb[0] = s_bb[1] = s_bb[2] = s_bb[3] = 0; }
         __syncthreads();
         int v = cnt;
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        if ((threadIdx.x & 31) == 0 && v) atomicAdd(&s_cnt, v);
+        for (int o = 16; o > 0; o >>= 1) {                   // warp-shuffle reductions: count and the four extrema
+            v += __shfl_xor_sync(0xffffffffu, v, o);
+            unsigned long long t;
+            t = __shfl_xor_sync(0xffffffffu, bb0, o); bb0 = t > bb0 ? t : bb0;
+            t = __shfl_xor_sync(0xffffffffu, bb1, o); bb1 = t > bb1 ? t : bb1;
+            t = __shfl_xor_sync(0xffffffffu, bb2, o); bb2 = t > bb2 ? t : bb2;
+            t = __shfl_xor_sync(0xffffffffu, bb3, o); bb3 = t > bb3 ? t : bb3;
+        }
+        if ((threadIdx.x & 31) == 0) {
+            if (v) atomicAdd(&s_cnt, v);
+            atomicMax(&s_bb[0], bb0); atomicMax(&s_bb[1], bb1); atomicMax(&s_bb[2], bb2); atomicMax(&s_bb[3], bb3);
+        }
         __syncthreads();
         if (threadIdx.x == 0 && s_cnt) atomicAdd(&sc->n_in, s_cnt);
+        if (threadIdx.x < 4 && s_bb[threadIdx.x]) atomicMax(&sc->bb[threadIdx.x], s_bb[threadIdx.x]);   // one atomic per block each
     }
 }
 
@@ -196,21 +233,6 @@ k_count_scan(const uint64_t* __restrict__ keys, int levels, DevScalars* __restri
 __global__ void __launch_bounds__(256) k_emit(BhTreeView t, int levels) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < t.n_in) bh_emit_body(t, levels, i);
-}
-
-// computeMass (BH.kt:173-202) bottom-up — bh_climb_body per in-tree body; also records the
-// preorder position of each body's leaf (leafpos, pre-filled with -1 for bodies not in the tree)
-__global__ void __launch_bounds__(256) k_climb(BhTreeView t, BhRoot root, const double* __restrict__ x,
-                                               const double* __restrict__ y, const double* __restrict__ m,
-                                               const int* __restrict__ jflag, int* __restrict__ leafpos) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= t.n_in) return;
-    const int b = t.order[i];
-    leafpos[b] = t.S[i + 1] + i;
-    if (i == 0) bh_write_terminal_cell(t);
-    // a body dropped by the jitter replay stays as a zero-mass ghost leaf (bh_jitter_cluster)
-    const double mb = (jflag && (jflag[b] & 1)) ? 0.0 : m[b];
-    bh_climb_body(t, root, i, x[b], y[b], mb);
 }
 
 // computeMass (BH.kt:173-202), block-local form.  A block owns CLIMB_B consecutive sorted bodies,
@@ -326,111 +348,91 @@ k_climb_top(BhTreeView t, BhRoot root, const BhClimbRoot* __restrict__ roots, co
     }
 }
 
-// accumulateForce (BH.kt:215-239) + ax = fx/m (BH.kt:390-391): one thread per target body.
-// Targets are the bodies [first_target, first_target + n_targets) in HOME order, which is the
-// Morton order of the last re-homing, so the lanes of a warp are spatial neighbours and the
-// body reads / acceleration writes are coalesced.  Stackless over the preorder cells.
-__global__ void __launch_bounds__(128)
+// accumulateForce (BH.kt:215-239) + ax = fx/m (BH.kt:390-391): one thread per G target bodies
+// (bh_walk_multi).  Targets are the bodies [first_target, first_target + n_targets) in HOME order, which is
+// the Morton order of the last re-homing, so the bodies of a thread and the lanes of a warp are spatial
+// neighbours and the body reads / acceleration writes are coalesced.  Stackless over the preorder cells.
+//
+// PERSISTENT, SM-AFFINE schedule.  ncu on a plain one-block-per-chunk launch: the walk waits on L1 misses
+// (a warp-wide record load touches ~16 sectors; at a 93 % sector hit rate most of those loads contain a
+// miss, i.e. an L2 or DRAM round trip on the pointer chase), because the blocks resident on one SM come
+// from all over the box.  Here the targets are cut into as many contiguous RANGES as there are SMs and
+// every warp takes its work (chunks of 32*G bodies, one atomic each) from the range of the SM it runs on
+// (%smid), so that all warps of an SM walk the same neighbourhood of the tree and share its cells in L1.
+// A warp whose range is exhausted STEALS: the lanes read all range counters at once, and the warp moves to
+// the next range (cyclically) that still has chunks — which also covers SMs that got no block of a small
+// grid and %smid values that skip numbers.  Work is handed out per WARP: no block-wide barriers.
+struct BhWalkQueue {
+    unsigned int* next;     // [n_ranges] counters, zero before the launch
+    int n_ranges;           // = SMs of the device (<= 1024)
+    int per;                // chunks per range (the last ranges may be short or empty)
+    int chunks;             // chunks in total
+};
+__device__ __forceinline__ int bh_walk_range_len(const BhWalkQueue& q, int r) {
+    const int left = q.chunks - r * q.per;
+    return left < 0 ? 0 : (left > q.per ? q.per : left);
+}
+
+template <int G, int ACC, int MINB>
+__global__ void __launch_bounds__(128, MINB)
 k_walk(BhTreeView t, BhWalkParams w, int first_target, int n_targets, const double* __restrict__ x,
-       const double* __restrict__ y, const double* __restrict__ m, const int* __restrict__ leafpos, double G,
+       const double* __restrict__ y, const double* __restrict__ m, const int* __restrict__ leafpos, double Gc,
        double* __restrict__ ax, double* __restrict__ ay, int* __restrict__ cntI, int* __restrict__ cntO,
-       DevScalars* __restrict__ sc, DevTotals* __restrict__ tot) {
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    int ni = 0, no = 0, nr = 0;
-    // every lane enters the walk (it contains full-warp votes); surplus lanes idle on the terminal record
-    const bool active = k < n_targets;
-    const int b = first_target + (active ? k : 0);
-    const BhWalkResult r = bh_walk_body(t, w, x[b], y[b], leafpos[b], active, (int)sc->pad);
-    if (active) {
-        const double mb = m[b];
-        // BH.kt:390-391 divides the force by b.m: a zero-mass body gets 0/0 = NaN
-        ax[b] = (mb == 0.0) ? nan("") : G * r.ax;
-        ay[b] = (mb == 0.0) ? nan("") : G * r.ay;
-        ni = r.interactions; no = r.opened; nr = r.retests;
-        if (cntI) { cntI[b] = ni; cntO[b] = no; }
-    }
+       DevScalars* __restrict__ sc, DevTotals* __restrict__ tot, BhWalkQueue q) {
+    const int lane = threadIdx.x & 31;
+    unsigned int smid;
+    asm("mov.u32 %0, %%smid;" : "=r"(smid));
+    int my = (int)(smid % (unsigned int)q.n_ranges);
+    const int zero = (int)sc->pad;
+    long long ni = 0, no = 0;
+    int nr = 0;
+    for (;;) {
+        int c = 0;
+        if (lane == 0) c = (int)atomicAdd(&q.next[my], 1u);
+        c = __shfl_sync(0xffffffffu, c, 0);
+        if (c >= bh_walk_range_len(q, my)) {
+            // this range is exhausted: the next one (cyclically) with unclaimed chunks, or done.  Lane l looks at the
+            // ranges my+1+l, my+1+l+32, ...; a range seen as exhausted stays exhausted, one seen as open may be
+            // exhausted by the time of the atomic above — then the scan simply runs again.
+            int found = -1;
+            for (int base = 0; base < q.n_ranges && found < 0; base += 32) {
+                const int k = base + lane;
+                int r = my + 1 + k;
+                if (r >= q.n_ranges) r -= q.n_ranges;
+                const bool open = k < q.n_ranges - 1 && *(volatile unsigned int*)&q.next[r] < (unsigned int)bh_walk_range_len(q, r);
+                const unsigned int bal = __ballot_sync(0xffffffffu, open);
+                if (bal) { found = my + 1 + base + (__ffs(bal) - 1); if (found >= q.n_ranges) found -= q.n_ranges; }
+            }
+            if (found < 0) break;
+            my = found;
+            continue;
+        }
+        const int chunk = my * q.per + c;
+        const int rel = (chunk * 32 + lane) * G;
+        int nactive = n_targets - rel;
+        nactive = nactive < 0 ? 0 : (nactive > G ? G : nactive);
+        double bx[G], by[G];
+        int self[G];
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        ni += __shfl_xor_sync(0xffffffffu, ni, o);
-        no += __shfl_xor_sync(0xffffffffu, no, o);
-        nr += __shfl_xor_sync(0xffffffffu, nr, o);
-    }
-    if ((threadIdx.x & 31) == 0) {
-        atomicAdd(&sc->interactions, (unsigned long long)ni);
-        atomicAdd(&sc->opened, (unsigned long long)no);
-        atomicAdd(&tot->interactions, (unsigned long long)ni);
-        atomicAdd(&tot->opened, (unsigned long long)no);
-        if (nr) { atomicAdd(&sc->retests, (unsigned long long)nr); atomicAdd(&tot->retests, (unsigned long long)nr); }
-    }
-}
-
-// The same evaluation with groups of WALK_LG adjacent lanes sharing one position (bh_walk_lanegroup).
-constexpr int WALK_LG = 4;
-__global__ void __launch_bounds__(128)
-k_walk_lanegroup(BhTreeView t, BhWalkParams w, int first_target, int n_targets, const double* __restrict__ x,
-                 const double* __restrict__ y, const double* __restrict__ m, const int* __restrict__ leafpos, double G,
-                 double* __restrict__ ax, double* __restrict__ ay, int* __restrict__ cntI, int* __restrict__ cntO,
-                 DevScalars* __restrict__ sc, DevTotals* __restrict__ tot) {
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    int ni = 0, no = 0, nr = 0;
-    const bool active = k < n_targets;
-    const bool group_active = (k & ~(WALK_LG - 1)) < n_targets;
-    const int b = first_target + (active ? k : 0);
-    const BhWalkResult r = bh_walk_lanegroup<WALK_LG>(t, w, x[b], y[b], leafpos[b], active, group_active, (int)sc->pad);
-    if (active) {
-        const double mb = m[b];
-        ax[b] = (mb == 0.0) ? nan("") : G * r.ax;      // BH.kt:390-391: 0/0 = NaN for m == 0
-        ay[b] = (mb == 0.0) ? nan("") : G * r.ay;
-        ni = r.interactions; no = r.opened; nr = r.retests;
-        if (cntI) { cntI[b] = ni; cntO[b] = no; }
-    }
+        for (int j = 0; j < G; ++j) {
+            const int b = first_target + (j < nactive ? rel + j : 0);
+            bx[j] = x[b]; by[j] = y[b]; self[j] = leafpos[b];
+        }
+        // every lane enters the walk (it contains full-warp votes); surplus lanes idle on the terminal record
+        BhMultiResult<G> r;
+        bh_walk_multi<G, ACC>(t, w, bx, by, self, nactive, zero, &r);
+        nr += r.retests;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        ni += __shfl_xor_sync(0xffffffffu, ni, o);
-        no += __shfl_xor_sync(0xffffffffu, no, o);
-        nr += __shfl_xor_sync(0xffffffffu, nr, o);
-    }
-    if ((threadIdx.x & 31) == 0) {
-        atomicAdd(&sc->interactions, (unsigned long long)ni);
-        atomicAdd(&sc->opened, (unsigned long long)no);
-        atomicAdd(&tot->interactions, (unsigned long long)ni);
-        atomicAdd(&tot->opened, (unsigned long long)no);
-        if (nr) { atomicAdd(&sc->retests, (unsigned long long)nr); atomicAdd(&tot->retests, (unsigned long long)nr); }
-    }
-}
-
-// The same evaluation with WALK_G bodies per thread (bh_walk_group): used when there are enough
-// targets to fill the machine with a quarter of the threads.
-constexpr int WALK_G = 4;
-template <bool ZERO_MASS>
-__global__ void __launch_bounds__(128)
-k_walk_group(BhTreeView t, BhWalkParams w, int first_target, int n_targets, const double* __restrict__ x,
-             const double* __restrict__ y, const double* __restrict__ m, const int* __restrict__ leafpos, double G,
-             double* __restrict__ ax, double* __restrict__ ay, int* __restrict__ cntI, int* __restrict__ cntO,
-             DevScalars* __restrict__ sc, DevTotals* __restrict__ tot) {
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    const int rel = k * WALK_G;
-    int nactive = n_targets - rel;
-    nactive = nactive < 0 ? 0 : (nactive > WALK_G ? WALK_G : nactive);
-    double bx[WALK_G], by[WALK_G];
-    int self[WALK_G];
-#pragma unroll
-    for (int j = 0; j < WALK_G; ++j) {
-        const int b = first_target + (j < nactive ? rel + j : 0);
-        bx[j] = x[b]; by[j] = y[b]; self[j] = leafpos[b];
-    }
-    BhGroupResult<WALK_G> r;
-    bh_walk_group<WALK_G, ZERO_MASS>(t, w, bx, by, self, nactive, (int)sc->pad, &r);
-    int ni = 0, no = 0, nr = r.retests;
-#pragma unroll
-    for (int j = 0; j < WALK_G; ++j) {
-        if (j < nactive) {
-            const int b = first_target + rel + j;
-            const double mb = m[b];
-            ax[b] = (mb == 0.0) ? nan("") : G * r.ax[j];    // BH.kt:390-391: 0/0 = NaN for m == 0
-            ay[b] = (mb == 0.0) ? nan("") : G * r.ay[j];
-            ni += r.interactions[j]; no += r.opened[j];
-            if (cntI) { cntI[b] = r.interactions[j]; cntO[b] = r.opened[j]; }
+        for (int j = 0; j < G; ++j) {
+            if (j < nactive) {
+                const int b = first_target + rel + j;
+                const double mb = m[b];
+                // BH.kt:390-391 divides the force by b.m: a zero-mass body gets 0/0 = NaN
+                ax[b] = (mb == 0.0) ? nan("") : Gc * r.ax[j];
+                ay[b] = (mb == 0.0) ? nan("") : Gc * r.ay[j];
+                ni += r.interactions[j]; no += r.opened[j];
+                if (cntI) { cntI[b] = r.interactions[j]; cntO[b] = r.opened[j]; }
+            }
         }
     }
 #pragma unroll
@@ -439,7 +441,7 @@ k_walk_group(BhTreeView t, BhWalkParams w, int first_target, int n_targets, cons
         no += __shfl_xor_sync(0xffffffffu, no, o);
         nr += __shfl_xor_sync(0xffffffffu, nr, o);
     }
-    if ((threadIdx.x & 31) == 0) {
+    if (lane == 0 && (ni | no | nr)) {
         atomicAdd(&sc->interactions, (unsigned long long)ni);
         atomicAdd(&sc->opened, (unsigned long long)no);
         atomicAdd(&tot->interactions, (unsigned long long)ni);
@@ -673,13 +675,6 @@ k_excl_scan(const int* __restrict__ in, int n, int* __restrict__ out, uint32_t* 
         const int64_t i = i0 + j;
         if (i < n) { out[i] = run; run += c[j]; if (i == n - 1) out[n] = run; }
     }
-}
-
-// any body with m == 0 ?  (zero-mass cells are pruned, BH.kt:216; a zero-mass target is NaN, :390)
-__global__ void k_flag_zero_mass(const double* __restrict__ m, int n, int* __restrict__ flag) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    const bool z = i < n && m[i] == 0.0;
-    if (__any_sync(0xffffffffu, z) && (threadIdx.x & 31) == 0) atomicOr(flag, 1);
 }
 
 // ---- merge ("devour") rule, BH.kt:463-532 ----------------------------------------------------

@@ -134,12 +134,9 @@ inline int bh_engine::finish_append(int64_t added) {
     BH_TRY(cudaMemsetAsync(ax, 0, (size_t)n * sizeof(double), st));
     BH_TRY(cudaMemsetAsync(ay, 0, (size_t)n * sizeof(double), st));
     BH_TRY(cudaMemsetAsync(dflags, 0, HF_COUNT * sizeof(int), st));
-    k_flag_zero_mass<<<grid_for(n, 256), 256, 0, st>>>(m, (int)n, dflags + HF_ZERO_MASS);
-    BH_TRY(cudaMemcpyAsync(hflags, dflags, HF_COUNT * sizeof(int), cudaMemcpyDeviceToHost, st));
     BH_TRY(cudaStreamSynchronize(st));
     BH_TRY(cudaGetLastError());
-    ctr.kernel_launches += 2;
-    any_zero_mass = hflags[HF_ZERO_MASS] != 0;
+    ctr.kernel_launches += 1;
     origin_identity = true;
     perm_identity = false;            // (kept simple: the combined permutation is treated as general)
     rehome_due = true;

@@ -117,6 +117,17 @@ class NativeEngine:
         self._check(self.lib.bh_get_bodies(self._h, n, *[_dp(a) for a in arrs], C.byref(n_out)), "bh_get_bodies")
         return arrs
 
+    def evaluate_slice(self):
+        """One evaluation of this rank's slice in the engine's current multi-GPU mode: (ax, ay, user_index)."""
+        n = self.n
+        ax, ay, ui = np.empty(n, np.float64), np.empty(n, np.float64), np.empty(n, np.int32)
+        k = C.c_int64()
+        self._check(self.lib.bh_evaluate_slice(self._h, n, _dp(ax), _dp(ay), _ip(ui), C.byref(k)), "bh_evaluate_slice")
+        return ax[:k.value], ay[:k.value], ui[:k.value]
+
+    def set_domain_mode(self, enabled: bool) -> None:
+        self._check(self.lib.bh_set_domain_mode(self._h, 1 if enabled else 0), "bh_set_domain_mode")
+
     def rebase_origin(self) -> None:
         """Make the current list the reference list of ``get_origin`` (after the caller has dropped
         the merged-away ``Body`` objects from its own list, BH.kt:519)."""

@@ -168,6 +168,131 @@ def run_reference(args, rank, world):
     emit(out)
 
 
+
+# ---- BASELINE.json configs[2..4] as device-generated scenes -------------------
+def build_config_scene(eng, name):
+    """Appends the bodies of config `name` with the device generators (bh_append_disk: BodyFactory.makeGalaxyDisk
+    laws, counter-based RNG keyed by the seed, so every rank generates the same list) and returns (W, H, label)."""
+    def disk(n, x, y, r, vx=0.0, vy=0.0, central=50_000.0, sat=5_000.0, seed=1):
+        p = eng.default_disk_params(2400, 800, x=x, y=y, r=r, vx=vx, vy=vy, central_mass=central, total_satellite_mass=sat)
+        eng.append_disk(n, p, seed=seed)
+    if name == "C3":      # 10M two-disk merger with central black holes: the reference scene (NBodyPanel.kt:83-99) x 800 bodies
+        W = H = 32768
+        eng.set_window(W, H)
+        k = math.sqrt(800.0)
+        disk(8_000_000, W * 0.5, H * 0.5, 300.0 * k, seed=4)
+        disk(2_000_000, W * 0.5, H * 0.5 - 240.0 * k, 100.0 * k, vx=-50.0, central=5_000.0, sat=500.0, seed=5)
+        return W, H, "10M-body two-disk galaxy merger with central black holes (8M + 2M, radii x sqrt(800))"
+    if name == "C4":      # 100M disk collision
+        W = H = 131072
+        eng.set_window(W, H)
+        r = 300.0 * math.sqrt(5000.0)
+        disk(50_000_000, W * 0.5 - 30_000.0, H * 0.5, r, vx=+50.0, seed=6)
+        disk(50_000_000, W * 0.5 + 30_000.0, H * 0.5, r, vx=-50.0, seed=7)
+        return W, H, "100M-body disk collision (2 x 50M, radii 21,213, closing at 100 px/t)"
+    if name == "C5":      # mixed-mass stress: 8 disks + 16 black holes, 50M bodies
+        W = H = 65536
+        eng.set_window(W, H)
+        rng = np.random.Generator(np.random.PCG64(8))
+        r = 300.0 * math.sqrt(6_250_000 / 10_000.0)
+        for d in range(8):
+            cx, cy = (0.15 + 0.7 * rng.random()) * W, (0.15 + 0.7 * rng.random()) * H
+            ang, v = rng.random() * 2 * math.pi, 50.0 * rng.random()
+            disk(6_250_000, cx, cy, r, vx=v * math.cos(ang), vy=v * math.sin(ang), seed=800 + d)
+        for b in range(16):   # the right-mouse-button "black hole": a lone 50,000-mass body (NBodyPanel.kt:171)
+            disk(1, (0.1 + 0.8 * rng.random()) * W, (0.1 + 0.8 * rng.random()) * H, 8.0, seed=900 + b)
+        return W, H, "mixed-mass stress: 8 disks x 6.25M + 16 black holes (50M bodies), theta stepped 0.5 -> 0.8 like Z/X key presses"
+    raise ValueError(name)
+
+
+def run_config(name, steps, warm, local_rank, rank, world, dist, allmax, allsum, barrier):
+    """One strong-scaling record of config `name` at this run's GPU count (total work fixed)."""
+    import bh_b200
+    n_total = {"C3": 10_000_000, "C4": 100_000_000, "C5": 50_000_016}[name]
+    eng = bh_b200.NativeEngine(device=local_rank, capacity_hint=n_total, flags=bh_b200.BH_FLAG_LET if world > 1 else 0)
+    try:
+        eng.set_params(theta=THETA, merge_min_dist=0.0)
+        if world > 1:
+            from bh_b200.distributed import init_nccl_engine
+            init_nccl_engine(eng, dist, rank, world)
+        W, H, label = build_config_scene(eng, name)
+        n = eng.n
+        rec = {"config": name, "workload": label, "bodies": n, "window": [W, H], "n_gpus": world, "scaling": "strong", "steps": steps, "warmup": warm}
+        e0 = None
+        if name == "C5":
+            e0 = eng.energy_tree(0.35)          # tree potential (O(N log N)); theta 0.35 for the diagnostic itself
+        eng.step(warm)
+        eng.reset_counters()
+        barrier()
+        dev_ms = 0.0
+        if name == "C5":                        # "adaptive theta": the Z/X keys step theta by 0.05 (NBodyPanel.kt:247-248)
+            theta, drift, done = THETA, [], 0
+            while done < steps:
+                k = min(10, steps - done)
+                eng.set_params(theta=theta)
+                eng.step(k)
+                dev_ms += eng.counters()["ms_step_call"]
+                done += k
+                theta = min(1.6, theta + 0.05)
+                if done % 50 == 0 or done == steps:
+                    e1 = eng.energy_tree(0.35)
+                    drift.append({"step": warm + done, "dE_over_E0": (e1["total"] - e0["total"]) / abs(e0["total"])})
+            rec["theta_schedule"] = "0.5 +0.05 every 10 steps"
+            rec["energy_drift_tree_potential"] = drift
+        else:
+            eng.step(steps)
+            dev_ms = eng.counters()["ms_step_call"]
+        barrier()
+        c = eng.counters()
+        dev_ms = allmax(dev_ms)
+        inter = allsum(float(c["total_interactions"]))
+        ne = max(1, c["total_evaluations"])
+        rec.update({"ms_per_step": dev_ms / steps, "steps_per_s": steps / (dev_ms * 1e-3), "interactions_per_s": inter / (dev_ms * 1e-3),
+                    "interactions_per_body_per_evaluation": inter / (2.0 * steps) / n,
+                    "phases_ms_per_evaluation": {"build": allmax(c["ms_build"]) / ne, "walk": allmax(c["ms_walk"]) / ne},
+                    "ms_per_step_exchange": allmax(c["ms_comm"]) / steps, "jitter_bodies_last_build": c["n_jitter_bodies"],
+                    "cells": c["n_cells"], "max_depth": c["max_depth"]})
+        if world > 1:
+            ls = eng.let_stats()
+            rec["mode"] = "domain (LET)" if ls["let_evaluations"] > 0 else "replicated tree"
+            rec["domain_mode_rank0"] = {k: ls[k] for k in ("let_evaluations", "fallbacks", "let_cells", "cells_imported", "own_strays")}
+        return rec
+    finally:
+        eng.close()
+
+
+def parity_check(eng, world, allsum, allmin):
+    """N > 1 self-check on the state the timed region left behind: this rank's slice evaluated in DOMAIN mode
+    (locally essential tree) and over the REPLICATED tree must give bit-identical accelerations, and the
+    interaction counts summed over the ranks must equal what ONE rank counts walking every body over the
+    replicated tree."""
+    eng.reset_counters()
+    ax_d, ay_d, ui_d = eng.evaluate_slice()
+    cd = eng.counters()
+    ls = eng.let_stats()
+    domain_ran = ls["let_evaluations"] > 0 and cd["total_evaluations"] == 1
+    eng.set_domain_mode(False)
+    eng.reset_counters()
+    ax_r, ay_r, ui_r = eng.evaluate_slice()
+    cr = eng.counters()
+    eng.reset_counters()
+    fx, fy = eng.compute_accelerations()              # every body, on every rank, over the replicated tree
+    cf = eng.counters()
+    eng.set_domain_mode(True)
+    same_slice = len(ui_d) == len(ui_r) and bool((ui_d == ui_r).all())
+    bit_dr = same_slice and bool(np.array_equal(ax_d, ax_r, equal_nan=True) and np.array_equal(ay_d, ay_r, equal_nan=True))
+    bit_full = bool(np.array_equal(ax_d, fx[ui_d], equal_nan=True) and np.array_equal(ay_d, fy[ui_d], equal_nan=True))
+    inter_d, inter_r = allsum(float(cd["interactions"])), allsum(float(cr["interactions"]))
+    open_d = allsum(float(cd["opened"]))
+    return {"mode": "domain (LET) vs replicated tree, same ranks, same state" if domain_ran else "replicated tree only (domain mode did not run)",
+            "bodies_checked_per_rank": int(len(ui_d)),
+            "interactions_equal": bool(inter_d == inter_r == float(cf["interactions"]) and open_d == float(cf["opened"])),
+            "interactions": {"domain_sum_over_ranks": inter_d, "replicated_sum_over_ranks": inter_r, "one_rank_all_bodies": float(cf["interactions"])},
+            "acc_bit_identical": bool(allmin(1.0 if (bit_dr and bit_full) else 0.0) == 1.0),
+            "acc_bit_identical_domain_vs_replicated_slice": bool(allmin(1.0 if bit_dr else 0.0) == 1.0),
+            "acc_bit_identical_vs_one_rank_walking_all_bodies": bool(allmin(1.0 if bit_full else 0.0) == 1.0)}
+
+
 def main():
     # rank 0 must print ONE JSON line on stdout: everything libraries print there (NCCL's version banner, ...)
     # is diverted to stderr; the line itself goes to the saved descriptor
@@ -182,6 +307,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--bodies", type=int, default=BODIES_PER_GPU, help="bodies per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--configs", default="C3,C4,C5", help="BASELINE.json configs measured after the headline (strong scaling); '' = none")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -216,6 +342,13 @@ def main():
             return v
         t = torch.tensor([v], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def allmin(v):
+        if world == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
         return float(t.item())
 
     def allsum(v):
@@ -267,14 +400,21 @@ def main():
     my_inter, my_open = float(c["total_interactions"]) / n_walks, float(c["total_opened"]) / n_walks
     walk_flops = 14.0 * my_inter + 8.0 * my_open           # 14 flop/interaction + 8 flop/rejected test
     ach = walk_flops / (c["ms_walk"] / n_walks * 1e-3) / 1e12
-    # dram__bytes_read.sum + dram__bytes_write.sum of one k_walk launch of this workload
-    # (profiles/r01c_ncu_full_walk_v2.txt); only valid for the default 1M-body N=1 workload
-    traffic = 88.8e6 if (world == 1 and args.bodies == BODIES_PER_GPU) else None
+    # dram__bytes_read.sum + dram__bytes_write.sum of one k_walk launch: taken from the ncu capture of THIS code on
+    # THIS workload when one is committed (profiles/walk_traffic.json names the capture it summarises), else null
+    traffic, traffic_src = None, None
+    tpath = os.path.join(ROOT, "profiles", "walk_traffic.json")
+    if world == 1 and args.bodies == BODIES_PER_GPU and os.path.exists(tpath):
+        try:
+            tj = json.load(open(tpath))
+            traffic, traffic_src = float(tj["dram_bytes_per_launch"]), tj.get("source")
+        except Exception:
+            pass
     roofline = {"kernel": "k_walk", "bound": "fp32", "achieved": ach, "peak": float(fp32[0]), "unit": "TFLOP/s",
-                "frac": ach / float(fp32[0]) if fp32[0] > 0 else None, "traffic": traffic,
+                "frac": ach / float(fp32[0]) if fp32[0] > 0 else None, "traffic": traffic, "traffic_source": traffic_src,
                 "peak_source": "measured live: FFMA microbenchmark (bh_measure_fp32_tflops) — MEASURED_PEAKS.json has no FP32 figure; "
-                               "the walk is neither HBM- nor tensor-bound: ncu shows the L1 data stage at 90% of peak (DESIGN.md §4)",
-                "l1_data_stage_pct_of_peak_ncu": 90.1, "hbm_bytes_algorithmic": 32.0 * n / world + 32.0 * c["n_cells"],
+                               "the walk is neither HBM- nor tensor-bound (ncu summaries under profiles/, DESIGN.md §4)",
+                "hbm_bytes_algorithmic": 32.0 * n / world + 32.0 * c["n_cells"],
                 "ms_per_launch": c["ms_walk"] / n_walks,
                 "algorithmic": "14 flop x interactions + 8 flop x rejected opening tests per launch"}
     # the HBM-bound phase: keygen + onesweep sort + scan + emit + climb (algorithmic bytes/body)
@@ -319,6 +459,22 @@ def main():
            "api": "bh_step_io(1, host in, host out) per step: resetBodies + step + getBodies, pinned host arrays, copies overlapped with compute",
            "steps_per_s_separate_calls": e2e_steps / seq_wall}
 
+    # ---- N > 1: the run checks itself (domain mode vs replicated tree vs one rank walking every body) -----------
+    pcheck = None
+    if world > 1:
+        pcheck = parity_check(eng, world, allsum, allmin)
+    eng.close()
+
+    # ---- BASELINE.json configs[2..4] at this GPU count (strong scaling: the total is fixed) --------------------
+    cfg_records = []
+    for name in [c for c in args.configs.split(",") if c]:
+        steps_c, warm_c = {"C3": (20, 3), "C4": (8, 2), "C5": (60, 2)}[name]
+        try:
+            cfg_records.append(run_config(name, steps_c, warm_c, local_rank, rank, world, dist, allmax, allsum, barrier))
+        except Exception as ex:                                   # a config must never take the headline down with it
+            cfg_records.append({"config": name, "n_gpus": world, "error": f"{type(ex).__name__}: {ex}"[:300]})
+            torch.cuda.synchronize()
+
     # ---- opt-in BH_FLAG_REUSE_ACC (result-identical, one evaluation per step): reported, not the headline
     reuse = None
     if world == 1:
@@ -347,6 +503,26 @@ def main():
         c1 = {"workload": "reference two-disk scene, 12,500 bodies, theta=0.5, merge rule on", "steps_per_s": 300 / (time.perf_counter() - t0),
               "bodies_left": e1.n}
         e1.close()
+
+    # ---- the device accuracy oracle (tiled all-pairs direct sum, BH.kt:250-259 over every pair): FP32-pipe roofline
+    direct = None
+    if rank == 0 and world == 1:
+        direct = []
+        for nd in (100_000, 1_000_000):
+            if nd > n:
+                continue
+            ed = bh_b200.NativeEngine(device=local_rank, capacity_hint=nd)
+            ed.set_window(W, H)
+            ed.set_params(theta=THETA, merge_min_dist=0.0)
+            ed.set_bodies(*[np.ascontiguousarray(a[:nd]) for a in scene])
+            ed.direct_sum()
+            ed.direct_sum()
+            ms = ed.counters()["ms_direct"]
+            tf = 14.0 * nd * (nd - 1) / (ms * 1e-3) / 1e12
+            direct.append({"kernel": "k_direct", "bodies": nd, "ms": ms, "pair_interactions_per_s": nd * (nd - 1) / (ms * 1e-3), "bound": "fp32",
+                           "achieved": tf, "peak": float(fp32[0]), "unit": "TFLOP/s", "frac": tf / float(fp32[0]) if fp32[0] > 0 else None,
+                           "algorithmic": "14 flop x N(N-1) pair interactions (SURVEY.md 8(d)); same measured FFMA peak as the walk"})
+            ed.close()
 
     # ---- CPU baseline beside it (rank 0, N = 1 only) ------------------------------------------
     cpu = None
@@ -384,6 +560,7 @@ def main():
             "phases_ms_per_evaluation": {"build": build_ms, "walk": walk_ms},
             "ms_per_step_other": {"exchange": c["ms_comm"] / args.steps, "integrate_and_rest": c["ms_integrate"] / args.steps},
             "roofline": roofline, "roofline_build": roofline_build, "cpu_baseline": cpu, "e2e": e2e, "configs0": c1, "reuse_acc_mode": reuse,
+            "parity_check": pcheck, "configs": cfg_records, "roofline_direct": direct,
             "gpu_launches": launches, "clocks": clocks,
         }
         if let_stats:
@@ -391,6 +568,8 @@ def main():
         emit(line)
     if world > 1:
         dist.destroy_process_group()
+    if pcheck is not None and not (pcheck["interactions_equal"] and pcheck["acc_bit_identical"]):
+        sys.exit(3)                                               # a multi-GPU run that disagrees with itself is not a result
 
 
 if __name__ == "__main__":

@@ -116,6 +116,13 @@ typedef struct bh_counters {
     double  ms_step_call;       /* device time (CUDA events on the engine's stream) of */
                                 /*   the most recent bh_step call, all its steps       */
     int64_t kernel_launches;    /* CUDA kernels launched since bh_reset_counters       */
+    double  bbox_min_x, bbox_max_x, bbox_min_y, bbox_max_y;
+                                /* bounding box of ALL bodies seen by the last build (a min/max
+                                 * reduction fused into the key generation).  The reference's root
+                                 * box is the window (BarnesHutAlg.kt:360-361), not this box: bodies
+                                 * outside the root are dropped by :126, so a box that pokes out of
+                                 * the root is the diagnosis behind n_out_of_box > 0.  NaN when empty. */
+    double  ms_direct;          /* device time of the most recent bh_direct_sum kernel */
 } bh_counters;
 
 /* ---- lifecycle ---------------------------------------------------------- */
@@ -307,6 +314,15 @@ int bh_export_slice(bh_engine* e, int32_t field, int64_t cap, double* a, double*
                     int64_t* lo, int64_t* hi);
 /* the concatenation of every rank's exported slice (n = bh_num_bodies doubles each) */
 int bh_import_slices(bh_engine* e, int32_t field, int64_t n, const double* a, const double* b);
+
+/* One force evaluation (buildTree + computeAccelerations, BarnesHutAlg.kt:359-366 + :374-395) of THIS RANK'S
+ * slice of targets, in the multi-GPU mode the engine is in (domain mode / replicated tree), without
+ * integrating: ax/ay[k] for the k-th body of the slice, user_index[k] = its position in the `bodies` list.
+ * With bh_set_domain_mode this is the self-check of a multi-GPU run: the same state evaluated in both modes
+ * must give bit-identical accelerations and equal interaction counts (bench.py `parity_check`). */
+int bh_evaluate_slice(bh_engine* e, int64_t cap, double* ax, double* ay, int32_t* user_index, int64_t* n_slice);
+/* switch the domain mode (BH_FLAG_LET) on/off at run time; takes effect at the next evaluation */
+int bh_set_domain_mode(bh_engine* e, int32_t enabled);
 
 /* ---- diagnostics ---------------------------------------------------------- */
 

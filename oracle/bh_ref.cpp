@@ -229,6 +229,16 @@ struct bh_engine {
         arena.clear();
         rootStore.init(Quad{par.root_cx, par.root_cy, par.root_half});
         BHTree* root = &rootStore;
+        // observer (not part of the reference): bounding box of all bodies, as the build finds them
+        double lox = std::nan(""), hix = std::nan(""), loy = std::nan(""), hiy = std::nan("");
+        for (const auto& b : bodies) {
+            if (b.x != b.x || b.y != b.y) continue;
+            if (!(lox <= b.x)) lox = b.x;
+            if (!(hix >= b.x)) hix = b.x;
+            if (!(loy <= b.y)) loy = b.y;
+            if (!(hiy >= b.y)) hiy = b.y;
+        }
+        ctr.bbox_min_x = lox; ctr.bbox_max_x = hix; ctr.bbox_min_y = loy; ctr.bbox_max_y = hiy;
         for (auto& b : bodies) root->insert(&b, arena);
         root->computeMass();
         ctr.ms_build += now_ms() - t0;
@@ -815,6 +825,25 @@ int bh_import_slices(bh_engine* e, int32_t field, int64_t n, const double* a, co
     if (field == BH_FIELD_POS) e->lastTree = nullptr;
     return BH_OK;
 }
+int bh_evaluate_slice(bh_engine* e, int64_t cap, double* ax, double* ay, int32_t* user_index, int64_t* n_slice) {
+    if (!e) return BH_E_ARG;
+    int64_t lo, hi;
+    e->mySlice(&lo, &hi);
+    if (n_slice) *n_slice = hi - lo;
+    if (cap < hi - lo) return fail(e, BH_E_ARG, "bh_evaluate_slice: capacity too small");
+    const size_t n = e->bodies.size();
+    std::vector<double> fx(n), fy(n);
+    const int rc = bh_compute_accelerations(e, fx.data(), fy.data());   // the port evaluates every body
+    if (rc != BH_OK) return rc;
+    for (int64_t k = lo; k < hi; ++k) {
+        if (ax) ax[k - lo] = fx[(size_t)k];
+        if (ay) ay[k - lo] = fy[(size_t)k];
+        if (user_index) user_index[k - lo] = (int32_t)k;
+    }
+    return BH_OK;
+}
+int bh_set_domain_mode(bh_engine* e, int32_t) { return e ? BH_OK : BH_E_ARG; }   // the port has no domain mode
+
 int bh_slice_bounds(int64_t n, int32_t world, int32_t rank, int64_t* lo, int64_t* hi) {
     if (n < 0 || world < 1 || rank < 0 || rank >= world || !lo || !hi) return BH_E_ARG;
     const int64_t per = (n + world - 1) / world;

@@ -54,7 +54,10 @@ def _run_facade_against_oracle(lib, oracle_lib, steps, exact):
         if exact:
             assert (st == ref).all(), s
         else:
-            assert np.abs(st[:2] - ref[:2]).max() < 1e-6 * (s + 1), s
+            # FP32 interactions: 1e-5 of the acceleration, i.e. of the velocity change per step (dt = 0.005, up to
+            # |a| ~ 1e5 beside the 50,000-mass centre); positions follow
+            assert np.abs(st[2:] - ref[2:]).max() < 2e-5 * np.abs(ref[2:]).max() * (s + 1), s
+            assert np.abs(st[:2] - ref[:2]).max() < 1e-4 * (s + 1), s
         # the device state IS the host state after every step (the round-1 bug re-seeded the device with t, not t+dt)
         dx, dy, dvx, dvy, dm = eng.native.get_bodies()
         assert (dx == st[0]).all() and (dy == st[1]).all() and (dvx == st[2]).all() and (dvy == st[3]).all() and (dm == bm).all(), s

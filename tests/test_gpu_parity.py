@@ -13,6 +13,7 @@ import math
 import numpy as np
 import pytest
 
+import bh_b200
 from bh_b200 import scenes
 from conftest import ACC_TOL, acc_errors, assert_acc_parity, key_levels, leaf_paths, make_engine
 
@@ -556,3 +557,67 @@ def test_step_io_equals_set_step_get(oracle_lib, cuda_lib):
     o = make_engine(oracle_lib, ms, theta=0.5, merge_min_dist=8.0)
     og, oo = g.step_io(3, inputs=ms), o.step_io(3, inputs=ms)
     assert len(og[0]) == len(oo[0]) < len(ms[0]) and (og[4] == oo[4]).all()
+
+
+WALK_VARIANTS = [(1, 0), (1, 1), (2, 1)]
+
+
+@pytest.mark.gpu
+def test_walk_variants_group_size_and_summation(oracle_lib, cuda_lib, monkeypatch):
+    """k_walk<G, ACC>: one body per lane with FP32 partial sums folded into f64 (what small target counts use), one
+    body per lane with every term added to an f64 sum at once, and PAIRS of bodies per thread sharing one preorder
+    position (bh_walk_multi; what large target counts use).  Every variant makes the reference's per-body decisions
+    (interaction and opened counts equal to the oracle's as integers), and the two f64 variants are BIT-IDENTICAL:
+    a body's result does not depend on its partner, which is what keeps any multi-GPU partition of the targets
+    bit-identical to one GPU.  Scenes: cloud, two disks with out-of-box and zero-mass bodies, theta 0.3 .. 1.0."""
+    scenes_ = [
+        ("cloud 60k", scenes.snap_f32(scenes.make_uniform_random(60_000, 0.5, seed=71)), 0.5),
+        ("two disks 30k + specials", None, 0.3),
+        ("cloud 20k theta 1.0", scenes.snap_f32(scenes.make_uniform_random(20_000, 0.5, seed=72)), 1.0),
+    ]
+    s = [a.copy() for a in scenes.snap_f32(scenes.default_two_disks(n1=24_000, n2=6_000, seed=73))]
+    s[0][100:110] = np.linspace(-500.0, -50.0, 10)      # outside the root box: targets only (BH.kt:126)
+    s[4][200:220] = 0.0                                  # zero mass: pruned as sources, NaN as targets (BH.kt:216,390)
+    scenes_[1] = (scenes_[1][0], tuple(s), 0.3)
+    for name, scene, theta in scenes_:
+        o = make_engine(oracle_lib, scene, theta=theta, flags=bh_b200.BH_FLAG_BODY_COUNTS)
+        ox, oy = o.compute_accelerations()
+        oi, oo = o.body_counts()
+        res = {}
+        for g, acc in WALK_VARIANTS:
+            monkeypatch.setenv("BH_WALK_G", str(g))
+            monkeypatch.setenv("BH_WALK_ACC", str(acc))
+            e = make_engine(cuda_lib, scene, theta=theta, flags=bh_b200.BH_FLAG_BODY_COUNTS)
+            gx, gy = e.compute_accelerations()
+            gi, go = e.body_counts()
+            assert (gi == oi).all() and (go == oo).all(), (name, g, acc)
+            ok = np.isfinite(ox)
+            assert (np.isnan(gx) == ~ok).all(), (name, g, acc)
+            assert_acc_parity(ox[ok], oy[ok], gx[ok], gy[ok], what=f"{name} G={g} acc={acc}")
+            res[(g, acc)] = (gx, gy)
+            e.close()
+        assert np.array_equal(res[(2, 1)][0], res[(1, 1)][0], equal_nan=True), name
+        assert np.array_equal(res[(2, 1)][1], res[(1, 1)][1], equal_nan=True), name
+        o.close()
+    monkeypatch.delenv("BH_WALK_G")
+    monkeypatch.delenv("BH_WALK_ACC")
+
+
+def test_bounding_box_reduction_matches_oracle(oracle_lib, cuda_lib):
+    """north_star's bounding-box reduction, fused into k_keygen (warp shuffles, one atomic per block and extremum):
+    exact min/max of all bodies, in the root box or not; the reference's root stays the window (BH.kt:360-361)."""
+    s = [a.copy() for a in scenes.snap_f32(scenes.default_two_disks(n1=20_000, n2=5_000, seed=77))]
+    s[0][7], s[1][7] = -812.25, 5000.5          # far outside the root box [-2, 2402) x [-802, 1602)
+    s[0][9], s[1][9] = 9000.0, -3000.125
+    g = make_engine(cuda_lib, tuple(s), theta=0.5)
+    o = make_engine(oracle_lib, tuple(s), theta=0.5)
+    g.build_tree()
+    o.build_tree()
+    gc, oc = g.counters(), o.counters()
+    for k in ("bbox_min_x", "bbox_max_x", "bbox_min_y", "bbox_max_y"):
+        assert gc[k] == oc[k], k
+    assert gc["bbox_min_x"] == -812.25 and gc["bbox_max_x"] == 9000.0 and gc["bbox_min_y"] == -3000.125 and gc["bbox_max_y"] == 5000.5
+    assert gc["n_out_of_box"] == oc["n_out_of_box"] == 2
+    e = make_engine(cuda_lib, tuple(a[:0] for a in s), theta=0.5)
+    e.build_tree()
+    assert math.isnan(e.counters()["bbox_min_x"])
