@@ -117,6 +117,9 @@ SYMBOLS = {
     "bh_step_finish": (C.c_int, [_H]),
     "bh_export_slice": (C.c_int, [_H, C.c_int32, C.c_int64, _D, _D, _I64, _I64]),
     "bh_import_slices": (C.c_int, [_H, C.c_int32, C.c_int64, _D, _D]),
+    "bh_get_slice_index": (C.c_int, [_H, C.c_int64, _I32, _I64]),
+    "bh_slice_epoch": (C.c_int64, [_H]),
+    "bh_step_io_slice": (C.c_int, [_H, C.c_int32, C.c_int64, _D, _D, _D, _D, _D, C.c_int64, _D, _D, _D, _D, _D, _I64]),
     "bh_evaluate_slice": (C.c_int, [_H, C.c_int64, _D, _D, _I32, _I64]),
     "bh_set_domain_mode": (C.c_int, [_H, C.c_int32]),
     "bh_measure_fp32_tflops": (C.c_int, [C.c_int32, _D]),

@@ -201,31 +201,46 @@ BH_HD void bh_split(double v, float* hi, float* lo) {
     *lo = (float)(v - (double)h);
 }
 
+// Sorted keys / scan values behind an accessor (the searches below are templated on it).
+struct BhKeysGlobal {
+    const uint64_t* __restrict__ keys;
+    const int* __restrict__ S;
+    BH_HD uint64_t key(int j) const { return keys[j]; }
+    BH_HD int scan(int j) const { return S[j]; }
+};
 // last index j >= from (from is known to be inside) whose key shares the prefix
 // (key >> sh) == pref; keys sorted ascending, n = number of in-tree keys
-BH_HD int bh_gallop_right(const uint64_t* __restrict__ keys, int n, int from, uint64_t pref, int sh) {
+template <class K>
+BH_HD int bh_gallop_right(const K& k, int n, int from, uint64_t pref, int sh) {
     int j = from;
     int step = 1;
-    while (j + step < n && (keys[j + step] >> sh) == pref) { j += step; step <<= 1; }
+    while (j + step < n && (k.key(j + step) >> sh) == pref) { j += step; step <<= 1; }
     int out = (j + step < n) ? (j + step) : n;   // first index known to be outside (or n)
     while (out - j > 1) {
         const int mid = j + ((out - j) >> 1);
-        if ((keys[mid] >> sh) == pref) j = mid; else out = mid;
+        if ((k.key(mid) >> sh) == pref) j = mid; else out = mid;
     }
     return j;
 }
 
 // first index j <= from whose key shares the prefix
-BH_HD int bh_gallop_left(const uint64_t* __restrict__ keys, int from, uint64_t pref, int sh) {
+template <class K>
+BH_HD int bh_gallop_left(const K& k, int from, uint64_t pref, int sh) {
     int j = from;
     int step = 1;
-    while (j - step >= 0 && (keys[j - step] >> sh) == pref) { j -= step; step <<= 1; }
+    while (j - step >= 0 && (k.key(j - step) >> sh) == pref) { j -= step; step <<= 1; }
     int out = (j - step >= 0) ? (j - step) : -1;  // last index known to be outside (or -1)
     while (j - out > 1) {
         const int mid = out + ((j - out) >> 1);
-        if ((keys[mid] >> sh) == pref) j = mid; else out = mid;
+        if ((k.key(mid) >> sh) == pref) j = mid; else out = mid;
     }
     return j;
+}
+BH_HD int bh_gallop_right(const uint64_t* __restrict__ keys, int n, int from, uint64_t pref, int sh) {
+    return bh_gallop_right(BhKeysGlobal{keys, nullptr}, n, from, pref, sh);
+}
+BH_HD int bh_gallop_left(const uint64_t* __restrict__ keys, int from, uint64_t pref, int sh) {
+    return bh_gallop_left(BhKeysGlobal{keys, nullptr}, from, pref, sh);
 }
 
 // shift that isolates the first d digits of a key
@@ -305,28 +320,29 @@ static inline int bh_host_fetch_add(int* p, int v) { const int o = *p; *p = o + 
 // Skeleton of everything body i "owns" in the preorder array: the column of internal
 // cells whose leftmost key is key[i], and the leaf of body i.  Pure function of the sorted
 // keys and S (no atomics); one thread per in-tree body.
-BH_HD void bh_emit_body(const BhTreeView& t, int levels, int i) {
+template <class K>
+BH_HD void bh_emit_body(const BhTreeView& t, const K& ks, int levels, int i) {
     const int n = t.n_in;
-    const uint64_t k = t.keys[i];
-    const int dprev = (i > 0) ? bh_common_levels(t.keys[i - 1], k, levels) : -1;
-    const int dnext = (i + 1 < n) ? bh_common_levels(k, t.keys[i + 1], levels) : -1;
-    const int base = t.S[i] + i;
+    const uint64_t k = ks.key(i);
+    const int dprev = (i > 0) ? bh_common_levels(ks.key(i - 1), k, levels) : -1;
+    const int dnext = (i + 1 < n) ? bh_common_levels(k, ks.key(i + 1), levels) : -1;
+    const int base = ks.scan(i) + i;
     // parent of the first entry of this group: the depth-dprev cell holding key[i-1] and key[i]
     int headParent = -1;
     if (i > 0) {
         const int sh = bh_prefix_shift(levels, dprev);
-        const int il = bh_gallop_left(t.keys, i, k >> sh, sh);
-        const int dl = (il > 0) ? bh_common_levels(t.keys[il - 1], t.keys[il], levels) : -1;
-        headParent = t.S[il] + il + (dprev - dl - 1);
+        const int il = bh_gallop_left(ks, i, k >> sh, sh);
+        const int dl = (il > 0) ? bh_common_levels(ks.key(il - 1), ks.key(il), levels) : -1;
+        headParent = ks.scan(il) + il + (dprev - dl - 1);
     }
     const int ncol = (dnext > dprev) ? (dnext - dprev) : 0;
     int hi = i;
     for (int d = dnext; d > dprev; --d) {   // deepest first: hi only grows
         const int sh = bh_prefix_shift(levels, d);
-        hi = bh_gallop_right(t.keys, n, hi, k >> sh, sh);
+        hi = bh_gallop_right(ks, n, hi, k >> sh, sh);
         const int p = base + (d - dprev - 1);
         BhCellS c;
-        c.skip = t.S[hi + 1] + hi + 1;
+        c.skip = ks.scan(hi + 1) + hi + 1;
         c.parent = (d == dprev + 1) ? headParent : (p - 1);
         c.cnt = hi - i + 1;
         c.level = d;
@@ -340,6 +356,7 @@ BH_HD void bh_emit_body(const BhTreeView& t, int levels, int i) {
     c.level = ((dprev > dnext) ? dprev : dnext) + 1;
     t.sk[lp] = c;
 }
+BH_HD void bh_emit_body(const BhTreeView& t, int levels, int i) { bh_emit_body(t, BhKeysGlobal{t.keys, t.S}, levels, i); }
 
 BH_HD void bh_write_cell(const BhTreeView& t, int p, double cx, double cy, double m, int skip, int level, bool leaf,
                          double half) {

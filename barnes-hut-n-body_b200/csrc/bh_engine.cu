@@ -133,6 +133,7 @@ struct bh_engine {
     int rank = 0, world = 1;
     bhcomm::Comm comm = nullptr;
     bool vel_valid = true;           // velocities of ALL bodies are current on this rank
+    bool mass_valid = true;          // masses of ALL bodies are current on this rank (bh_step_io_slice replaces a slice only)
     int phase = 0;                   // 0 idle, 1 after step_begin, 2 after step_end
     bool acc_valid = false;          // ax/ay of this rank's slice = a(current positions, current params)
     bh_params acc_par{};             // parameters acc_valid refers to
@@ -142,7 +143,7 @@ struct bh_engine {
     int64_t io_cap = 0;
     cudaEvent_t io_ev[2]{};          // [0] (vx, vy, m) arrived, [1] final positions written
     bool io_wait_in = false;         // the compute stream has not yet waited for (vx, vy, m)
-    struct IoOut { double *x = nullptr, *y = nullptr, *m = nullptr; bool armed = false; } io_out;
+    struct IoOut { double *x = nullptr, *y = nullptr, *m = nullptr; bool armed = false, slice = false; int64_t epoch = -1; } io_out;
     int wait_inputs() {              // before the first kernel that reads vx / vy / m
         if (io_wait_in) {
             const cudaError_t ce = cudaStreamWaitEvent(st, io_ev[0], 0);
@@ -310,11 +311,11 @@ struct bh_engine {
                 const size_t cnt = (size_t)(let.cut[r + 1] - let.cut[r]);
                 if (cnt == 0) continue;
                 rc = A.Broadcast(a + let.cut[r], a + let.cut[r], cnt, bhcomm::kFloat64, r, comm, st);
-                if (rc == bhcomm::kSuccess) rc = A.Broadcast(b + let.cut[r], b + let.cut[r], cnt, bhcomm::kFloat64, r, comm, st);
+                if (rc == bhcomm::kSuccess && b) rc = A.Broadcast(b + let.cut[r], b + let.cut[r], cnt, bhcomm::kFloat64, r, comm, st);
             }
         } else {
             if (rc == bhcomm::kSuccess) rc = A.AllGather(a + (size_t)rank * per, a, per, bhcomm::kFloat64, comm, st);
-            if (rc == bhcomm::kSuccess) rc = A.AllGather(b + (size_t)rank * per, b, per, bhcomm::kFloat64, comm, st);
+            if (rc == bhcomm::kSuccess && b) rc = A.AllGather(b + (size_t)rank * per, b, per, bhcomm::kFloat64, comm, st);
         }
         const int rc2 = A.GroupEnd();
         if (rc == bhcomm::kSuccess) rc = rc2;
@@ -333,13 +334,23 @@ struct bh_engine {
         return BH_OK;
     }
 
+    // every rank needs every body's mass (replicated build, re-homing)
+    int sync_masses() {
+        if (mass_valid || world <= 1) { mass_valid = true; return BH_OK; }
+        if (transport != T_NCCL) return fail(BH_E_STATE, "masses are not replicated");
+        BH_RC(all_gather_pair(m, nullptr));
+        mass_valid = true;
+        heavies_valid = false;
+        return BH_OK;
+    }
+
     // ---- buildTree(), BH.kt:359-366 ------------------------------------------------------
     int build(int slot = 0, bool timed = true) {
         tree_valid = false;
         let.view_valid = false;
         root = BhRoot{par.root_cx, par.root_cy, par.root_half, bh_key_levels(par.root_half)};
         const int nn = (int)n;
-        if (!let.local_build) BH_RC(sync_positions());        // a replicated build needs every body's position
+        if (!let.local_build) { BH_RC(sync_positions()); BH_RC(sync_masses()); }   // a replicated build needs every body's position and mass
         if (rehome_due && nn > 0) { BH_RC(sync_velocities()); BH_RC(wait_inputs()); }
         if (timed) BH_TRY(cudaEventRecord(ev[slot + 0], st));
         bool rehomed = false;
@@ -656,6 +667,18 @@ int bh_engine::emit_positions_out() {
     io_out.armed = false;
     BH_TRY(cudaEventRecord(io_ev[1], st));
     BH_TRY(cudaStreamWaitEvent(copy_st, io_ev[1], 0));
+    if (io_out.slice) {                      // bh_step_io_slice: this rank's slice as it lies in the home order
+        int64_t lo, hi;
+        my_slice(&lo, &hi);
+        io_out.epoch = ctr_rehomes;          // (a re-homing after this point re-orders the slice: the caller copies again)
+        const size_t bytes = (size_t)(hi - lo) * sizeof(double);
+        if (bytes) {
+            if (io_out.x) BH_TRY(cudaMemcpyAsync(io_out.x, x + lo, bytes, cudaMemcpyDeviceToHost, copy_st));
+            if (io_out.y) BH_TRY(cudaMemcpyAsync(io_out.y, y + lo, bytes, cudaMemcpyDeviceToHost, copy_st));
+            if (io_out.m) BH_TRY(cudaMemcpyAsync(io_out.m, m + lo, bytes, cudaMemcpyDeviceToHost, copy_st));
+        }
+        return BH_OK;
+    }
     const double* src[3] = {x, y, m};
     double* dst[3] = {io_out.x, io_out.y, io_out.m};
     for (int k = 0; k < 3; ++k) {
@@ -847,6 +870,7 @@ int bh_set_bodies(bh_engine* e, int64_t n, const double* x, const double* y, con
     e->tree_valid = false;
     e->heavies_valid = false;
     e->vel_valid = true;
+    e->mass_valid = true;
     e->acc_valid = false;
     e->let.pos_valid = true;
     e->let.part_valid = false; e->let.n_declined = -1;
@@ -1143,6 +1167,94 @@ int bh_step_io(bh_engine* e, int32_t nsteps, int64_t n_in, const double* x_in, c
     if (rc == BH_OK && (c1 != cudaSuccess || c2 != cudaSuccess)) rc = e->cuda_fail(c1 != cudaSuccess ? c1 : c2, "bh_step_io");
     if (n_out) *n_out = e->n;
     return rc;
+}
+
+int bh_get_slice_index(bh_engine* e, int64_t cap, int32_t* user_index, int64_t* n_slice) {
+    if (!e) return BH_E_ARG;
+    E_TRY(cudaSetDevice(e->device));
+    int64_t lo, hi;
+    e->my_slice(&lo, &hi);
+    if (n_slice) *n_slice = hi - lo;
+    if (cap < hi - lo) return e->fail(BH_E_ARG, "bh_get_slice_index: capacity too small");
+    if (user_index && hi > lo) {
+        E_TRY(cudaMemcpyAsync(user_index, e->perm + lo, (size_t)(hi - lo) * sizeof(int32_t), cudaMemcpyDeviceToHost, e->st));
+        E_TRY(cudaStreamSynchronize(e->st));
+    }
+    return BH_OK;
+}
+
+int64_t bh_slice_epoch(const bh_engine* e) { return e ? e->ctr_rehomes : 0; }
+
+int bh_step_io_slice(bh_engine* e, int32_t nsteps, int64_t n_in, const double* x_in, const double* y_in, const double* vx_in,
+                     const double* vy_in, const double* m_in, int64_t cap_out, double* x_out, double* y_out, double* vx_out,
+                     double* vy_out, double* m_out, int64_t* n_out) {
+    if (!e || nsteps < 0 || (x_in && (!y_in || !vx_in || !vy_in || !m_in)))
+        return e ? e->fail(BH_E_ARG, "bh_step_io_slice: bad arguments") : BH_E_ARG;
+    E_TRY(cudaSetDevice(e->device));
+    if (e->phase != 0) return e->fail(BH_E_STATE, "bh_step_io_slice: a step is in progress");
+    if (e->world > 1 && e->transport != bh_engine::T_NCCL) return e->fail(BH_E_STATE, "bh_step_io_slice: needs the NCCL transport");
+    if (e->world > 1 && e->merge_enabled()) return e->fail(BH_E_STATE, "bh_step_io_slice: the merge rule re-indexes the list on every rank; disable it (merge_min_dist <= 0)");
+    if (!e->copy_st) {
+        E_TRY(cudaStreamCreateWithFlags(&e->copy_st, cudaStreamNonBlocking));
+        E_TRY(cudaEventCreateWithFlags(&e->snap_ev[0], cudaEventDisableTiming));
+        E_TRY(cudaEventCreateWithFlags(&e->snap_ev[1], cudaEventDisableTiming));
+    }
+    if (!e->io_ev[0]) {
+        E_TRY(cudaEventCreateWithFlags(&e->io_ev[0], cudaEventDisableTiming));
+        E_TRY(cudaEventCreateWithFlags(&e->io_ev[1], cudaEventDisableTiming));
+    }
+    int64_t lo, hi;
+    e->my_slice(&lo, &hi);
+    if (x_in) {
+        if (n_in != hi - lo) return e->fail(BH_E_ARG, "bh_step_io_slice: n_in must be the length of this rank's slice (bh_get_slice_index)");
+        const size_t bytes = (size_t)(hi - lo) * sizeof(double);
+        if (bytes) {
+            // positions on the compute stream (the build starts on them); velocities and masses on the copy stream,
+            // behind whatever used the old ones — the compute stream waits for them where it first needs them
+            E_TRY(cudaMemcpyAsync(e->x + lo, x_in, bytes, cudaMemcpyHostToDevice, e->st));
+            E_TRY(cudaMemcpyAsync(e->y + lo, y_in, bytes, cudaMemcpyHostToDevice, e->st));
+            E_TRY(cudaEventRecord(e->io_ev[1], e->st));
+            E_TRY(cudaStreamWaitEvent(e->copy_st, e->io_ev[1], 0));
+            E_TRY(cudaMemcpyAsync(e->m + lo, m_in, bytes, cudaMemcpyHostToDevice, e->copy_st));
+            E_TRY(cudaMemcpyAsync(e->vx + lo, vx_in, bytes, cudaMemcpyHostToDevice, e->copy_st));
+            E_TRY(cudaMemcpyAsync(e->vy + lo, vy_in, bytes, cudaMemcpyHostToDevice, e->copy_st));
+            E_TRY(cudaEventRecord(e->io_ev[0], e->copy_st));
+            e->io_wait_in = true;
+        }
+        e->tree_valid = false; e->acc_valid = false; e->heavies_valid = false;
+        if (e->world > 1) { e->let.pos_valid = false; e->vel_valid = false; e->mass_valid = false; }
+    }
+    const bool want_out = x_out || y_out || vx_out || vy_out || m_out;
+    if (want_out && cap_out < hi - lo) return e->fail(BH_E_ARG, "bh_step_io_slice: capacity too small");
+    // the last drift triggers the read-back of the slice's (x, y, m) on the copy stream, under the last evaluation
+    e->io_out.x = x_out; e->io_out.y = y_out; e->io_out.m = m_out;
+    e->io_out.slice = true; e->io_out.epoch = -1;
+    e->io_out.armed = nsteps >= 1 && (x_out || y_out || m_out);
+    e->io_steps_left = nsteps;
+    int rc = e->run_steps(nsteps);
+    e->io_steps_left = 0;
+    e->io_out.armed = false; e->io_out.slice = false;
+    if (rc == BH_OK && e->io_wait_in) rc = e->wait_inputs();
+    if (rc != BH_OK) { cudaStreamSynchronize(e->copy_st); return rc; }
+    e->my_slice(&lo, &hi);                     // a re-homing inside the steps re-cuts the slices (bh_slice_epoch changed)
+    if (n_out) *n_out = hi - lo;
+    if (want_out && cap_out < hi - lo) { cudaStreamSynchronize(e->copy_st); return e->fail(BH_E_ARG, "bh_step_io_slice: capacity too small"); }
+    const size_t ob = (size_t)(hi - lo) * sizeof(double);
+    if (want_out && ob) {
+        // positions and masses again if they were not sent early, or were re-ordered (re-homing) or mutated (jitter) since
+        const bool again = e->io_out.epoch != e->ctr_rehomes || e->jitter_active || e->let.returns_applied;
+        if (again) {
+            E_TRY(cudaStreamSynchronize(e->copy_st));
+            if (x_out) E_TRY(cudaMemcpyAsync(x_out, e->x + lo, ob, cudaMemcpyDeviceToHost, e->st));
+            if (y_out) E_TRY(cudaMemcpyAsync(y_out, e->y + lo, ob, cudaMemcpyDeviceToHost, e->st));
+            if (m_out) E_TRY(cudaMemcpyAsync(m_out, e->m + lo, ob, cudaMemcpyDeviceToHost, e->st));
+        }
+        if (vx_out) E_TRY(cudaMemcpyAsync(vx_out, e->vx + lo, ob, cudaMemcpyDeviceToHost, e->st));
+        if (vy_out) E_TRY(cudaMemcpyAsync(vy_out, e->vy + lo, ob, cudaMemcpyDeviceToHost, e->st));
+    }
+    const cudaError_t c1 = cudaStreamSynchronize(e->st), c2 = cudaStreamSynchronize(e->copy_st);
+    if (c1 != cudaSuccess || c2 != cudaSuccess) return e->cuda_fail(c1 != cudaSuccess ? c1 : c2, "bh_step_io_slice");
+    return BH_OK;
 }
 
 int bh_build_tree(bh_engine* e) {
@@ -1478,6 +1590,11 @@ int bh_get_let_stats(bh_engine* e, int64_t* out, int32_t n_out) {
     int64_t v[40] = {e->let.enabled ? 1 : 0, e->let.part_valid ? 1 : 0, e->let.ell, e->let.evaluations, e->let.fallbacks,
                      e->let.M, e->let.last_imported, e->let.last_sent, e->let.last_strays, e->let.n_items};
     for (int k = 0; k < 7; ++k) v[10 + k] = 0;
+    v[10] = e->let.fb_jitter; v[11] = e->let.fb_strays; v[12] = e->let.fb_cells; v[13] = e->let.stray_cap; v[14] = e->let.jret_total;
+    if (e->let.dcnt) {   // diagnostics of the last evaluation: stray leaf look-ups by descent / by the fall-back scan
+        int dc[8] = {0};
+        if (cudaMemcpy(dc, e->let.dcnt, 8 * sizeof(int), cudaMemcpyDeviceToHost) == cudaSuccess) { v[15] = dc[4]; v[16] = dc[5]; }
+    }
     v[17] = e->let.n_folds;
     if (e->let.ipc_ok) v[0] = 2;   // enabled, blocks imported over peer memory
     for (int k = 0; k < 8; ++k) v[18 + k] = 0;

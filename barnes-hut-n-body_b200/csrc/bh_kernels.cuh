@@ -229,7 +229,9 @@ k_count_scan(const uint64_t* __restrict__ keys, int levels, DevScalars* __restri
     }
 }
 
-// cell skeletons (skip / parent / count / level) — bh_emit_body per in-tree body
+// cell skeletons (skip / parent / count / level) — bh_emit_body per in-tree body.  (Staging a block's keys and
+// scan values in shared memory for the galloping searches was measured: 81 us against 64 us for the plain
+// L2-resident arrays at 1M bodies, so the searches read the global arrays.)
 __global__ void __launch_bounds__(256) k_emit(BhTreeView t, int levels) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < t.n_in) bh_emit_body(t, levels, i);

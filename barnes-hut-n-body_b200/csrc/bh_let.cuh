@@ -45,7 +45,9 @@ __device__ __forceinline__ void let_atomic_max_d(double* p, double v) {
 //   [4..7] bounding box of the own bodies outside the root box  [8 .. 8+bw) footprint bitmap
 //   then cap x (x, y, m, user index)
 constexpr int LET_SEG_HDR = 8;
-enum { LET_D_STRAYS = 0, LET_D_GUESTS = 1, LET_D_FLAG = 2, LET_D_COUNT = 4 };
+enum { LET_D_STRAYS = 0, LET_D_GUESTS = 1, LET_D_FLAG = 2, LET_D_JRET = 3, LET_D_DESCENTS = 4, LET_D_SCANS = 5, LET_D_COUNT = 6 };
+// jitter-return slots per host rank behind the level summaries in the all-reduced table (see k_let_jitter_returns)
+constexpr int LET_JRET = 256;
 
 __global__ void k_let_seg_init(double* __restrict__ seg, int bw, int* __restrict__ dcnt) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -63,7 +65,7 @@ __global__ void __launch_bounds__(256)
 k_let_local(int n_own, const double* __restrict__ x, const double* __restrict__ y, const double* __restrict__ m,
             const int* __restrict__ perm, BhRoot root, BhGrid grid, int ell, int lam, uint32_t c_lo, uint32_t c_hi, int cap,
             double* __restrict__ lx, double* __restrict__ ly, double* __restrict__ lm, int* __restrict__ lperm,
-            double* __restrict__ seg, int bw, int* __restrict__ dcnt) {
+            double* __restrict__ seg, int bw, int* __restrict__ dcnt, int* __restrict__ stray_slot) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= n_own) return;
     const double px = x[j], py = y[j], pm = m[j];
@@ -89,6 +91,7 @@ k_let_local(int n_own, const double* __restrict__ x, const double* __restrict__ 
         if (k < cap) {
             double* e = seg + LET_SEG_HDR + bw + 4 * (size_t)k;
             e[0] = px; e[1] = py; e[2] = pm; e[3] = (double)pu;
+            stray_slot[k] = j;       // segment entry k is own body j (a host may send its position back, k_let_jitter_returns)
         }
     }
 }
@@ -103,7 +106,7 @@ __global__ void k_let_seg_header(double* __restrict__ seg, const int* __restrict
 __global__ void __launch_bounds__(256)
 k_let_guests(const double* __restrict__ segs, int64_t seg_len, int bw, int cap, int world, int me, BhRoot root, BhGrid grid,
              int ell, uint32_t c_lo, uint32_t c_hi, int n_own, int max_guests, double* __restrict__ lx, double* __restrict__ ly,
-             double* __restrict__ lm, int* __restrict__ lperm, int* __restrict__ dcnt) {
+             double* __restrict__ lm, int* __restrict__ lperm, int* __restrict__ dcnt, int* __restrict__ gsrc) {
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int q = (int)(t / cap), k = (int)(t % cap);
     if (q >= world || q == me) return;
@@ -117,15 +120,37 @@ k_let_guests(const double* __restrict__ segs, int64_t seg_len, int bw, int cap, 
     const int g = atomicAdd(&dcnt[LET_D_GUESTS], 1);
     if (g >= max_guests) return;   // cannot happen: max_guests = all strays of the other ranks
     lx[n_own + g] = px; ly[n_own + g] = py; lm[n_own + g] = e[2]; lperm[n_own + g] = (int)e[3];
+    gsrc[g] = q * cap + k;           // guest g is entry k of rank q's segment
 }
 
-// a guest inside a jitter cluster (BH.kt:145-156 would mutate a body this rank does not own)
-__global__ void k_let_jitter_check(const uint64_t* __restrict__ keys, const int* __restrict__ order, int n_in, int n_own,
-                                   int* __restrict__ flag) {
+// A guest inside a jitter cluster: the replay of BH.kt:145-156 on this (host) rank mutated a body another rank owns.
+// The mutated position goes back to its home rank in one of this rank's LET_JRET return slots behind the level
+// summaries of the all-reduced table: (count = 1, mass = home rank, comx/comy = new position, pos = entry of the
+// body in its home rank's segment).  More such guests than slots: retry flag (the evaluation is redone after a
+// re-homing, after which there are no strays).
+__global__ void k_let_jitter_returns(const uint64_t* __restrict__ keys, const int* __restrict__ order, int n_in, int n_own,
+                                     const double* __restrict__ lx, const double* __restrict__ ly, const int* __restrict__ gsrc,
+                                     int cap, BhLetEntry* __restrict__ slots, int* __restrict__ dcnt) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_in || order[i] < n_own) return;
     const uint64_t k = keys[i];
-    if ((i > 0 && keys[i - 1] == k) || (i + 1 < n_in && keys[i + 1] == k)) atomicOr(flag, 1);
+    if (!((i > 0 && keys[i - 1] == k) || (i + 1 < n_in && keys[i + 1] == k))) return;
+    const int j = atomicAdd(&dcnt[LET_D_JRET], 1);
+    if (j >= LET_JRET) { atomicOr(&dcnt[LET_D_FLAG], 1); return; }
+    const int b = order[i], src = gsrc[b - n_own];
+    BhLetEntry e;
+    e.count = 1.0; e.mass = (double)(src / cap); e.comx = lx[b]; e.comy = ly[b]; e.pos = (double)(src % cap); e.size = 0.0;
+    slots[j] = e;
+}
+// home side: take the positions the hosts sent back for this rank's strays (after the table all-reduce)
+__global__ void k_let_apply_returns(const BhLetEntry* __restrict__ slots, int n_slots, int me, const int* __restrict__ stray_slot,
+                                    double* __restrict__ x, double* __restrict__ y, double* __restrict__ lx, double* __restrict__ ly) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_slots) return;
+    const BhLetEntry e = slots[i];
+    if (e.count == 0.0 || (int)e.mass != me) return;
+    const int j = stray_slot[(int)e.pos];
+    x[j] = e.comx; y[j] = e.comy; lx[j] = e.comx; ly[j] = e.comy;
 }
 
 __global__ void k_let_summary(BhTreeView t, int levels, int ell, const double* __restrict__ lx, const double* __restrict__ ly,
@@ -139,9 +164,10 @@ __global__ void k_let_summary(BhTreeView t, int levels, int ell, const double* _
 // this rank's retry flag: a guest in a jitter cluster, or some rank had more strays than a segment holds
 __global__ void k_let_flag(BhLetEntry* __restrict__ e, const int* __restrict__ flag, const double* __restrict__ segs,
                            int64_t seg_len, int world) {
-    bool retry = *flag != 0;
-    for (int q = 0; q < world; ++q) retry |= segs[(size_t)q * seg_len + 1] != 0.0;
-    e->count = retry ? 1.0 : 0.0;
+    // reason bits: 1 = a guest in a jitter cluster, 2 = stray overflow on some rank, 4 = the local tree outgrew the cell arrays
+    int code = ((*flag & 1) ? 1 : 0) | ((*flag & 4) ? 4 : 0);
+    for (int q = 0; q < world; ++q) if (segs[(size_t)q * seg_len + 1] != 0.0) code |= 2;
+    e->count = (double)code;
 }
 
 struct LetSplit { uint32_t cs[17]; int world, me; };
@@ -250,10 +276,18 @@ __global__ void __launch_bounds__(1024) k_let_scans(LetScanJob job) {
 // the few numbers the host needs: items, LET cells, receive offset of every owner, send offset of every peer
 __global__ void k_let_collect(const int* __restrict__ item_first, uint32_t ncodes, const int* __restrict__ iS,
                               const int* __restrict__ iW, const int* __restrict__ recvoff, const int* __restrict__ sendoff,
-                              LetSplit sp, const int* __restrict__ dcnt, int* __restrict__ out) {
+                              LetSplit sp, const int* __restrict__ dcnt, int* __restrict__ out,
+                              const BhLetEntry* __restrict__ jret_slots) {
     const int t = threadIdx.x;
     const int n = item_first[ncodes];
-    if (t == 0) { out[0] = n; out[1] = iS[n] + iW[n]; out[38] = dcnt[LET_D_STRAYS]; out[39] = dcnt[LET_D_GUESTS]; }
+    {   // positions coming back for this rank's strays (k_let_apply_returns will change x / y of own bodies)
+        int mine = 0;
+        for (int i = t; i < sp.world * LET_JRET; i += 32) mine += (jret_slots[i].count != 0.0 && (int)jret_slots[i].mass == sp.me);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
+        if (t == 0) out[37] = mine;
+    }
+    if (t == 0) { out[0] = n; out[1] = iS[n] + iW[n]; out[36] = dcnt[LET_D_JRET]; out[38] = dcnt[LET_D_STRAYS]; out[39] = dcnt[LET_D_GUESTS]; }
     const uint32_t mylen = sp.cs[sp.me + 1] - sp.cs[sp.me];
     if (t <= sp.world) {
         out[2 + t] = recvoff[sp.cs[t]];
@@ -297,30 +331,46 @@ struct LetPeers { const BhCellD* cd[16]; const BhCellS* sk[16]; };
 
 // one warp per code: own blocks from the local arrays; imported blocks straight from the OWNER's local
 // arrays over NVLink peer memory (peers != nullptr), else from the receive buffer of the NCCL exchange
+// cells of a block are copied in CHUNKS of LET_BLK_CHUNK by one warp each: a level-ELL code of a dense galactic core
+// holds 10^5 bodies, and one warp per block (as the uniform cloud allowed) serialised the whole phase on it
+constexpr int LET_BLK_CHUNK = 256;
+__global__ void k_let_block_chunks(const int* __restrict__ nit, const int* __restrict__ blk, uint32_t ncodes, int* __restrict__ nchunk) {
+    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= ncodes) return;
+    const int B = blk[c];
+    nchunk[c] = (nit[c] == 2 && B > 1) ? (B - 1 + LET_BLK_CHUNK - 1) / LET_BLK_CHUNK : 0;
+}
 __global__ void __launch_bounds__(256)
-k_let_blocks(BhTreeView let, const BhLetEntry* __restrict__ table, uint32_t ncodes, LetSplit sp, const int* __restrict__ nit,
+k_let_blocks(BhTreeView let, const BhLetEntry* __restrict__ table, uint32_t ncodes, LetSplit sp, const int* __restrict__ chunkoff,
              const int* __restrict__ blk, const int* __restrict__ dst, const int* __restrict__ recvoff,
              const BhLetWire* __restrict__ recvbuf, const BhCellD* __restrict__ cd, const BhCellS* __restrict__ sk, double half,
              LetPeers peers, int use_peers) {
     const int64_t wid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
-    if (wid >= ncodes) return;
-    const uint32_t c = (uint32_t)wid;
+    if (wid >= chunkoff[ncodes]) return;
+    // the code of chunk `wid`: last c with chunkoff[c] <= wid (exclusive scan; codes without chunks repeat the value)
+    uint32_t lo = 0, hi = ncodes;
+    while (hi - lo > 1) {
+        const uint32_t mid = lo + ((hi - lo) >> 1);
+        if (chunkoff[mid] <= (int)wid) lo = mid; else hi = mid;
+    }
+    const uint32_t c = lo;
     const int B = blk[c];
-    if (nit[c] != 2 || B <= 1) return;
+    const int j0 = 1 + ((int)wid - chunkoff[c]) * LET_BLK_CHUNK;
+    const int j1 = min(B, j0 + LET_BLK_CHUNK);
     const int d = dst[c];
     if (c >= sp.cs[sp.me] && c < sp.cs[sp.me + 1]) {
         const int rp = (int)table[c].pos;
-        for (int j = 1 + lane; j < B; j += 32) bh_let_place(let, bh_let_wire(cd, sk, rp + j, rp), d, j, half);
+        for (int j = j0 + lane; j < j1; j += 32) bh_let_place(let, bh_let_wire(cd, sk, rp + j, rp), d, j, half);
     } else if (use_peers) {
         const int o = let_owner(sp, c);
         const BhCellD* __restrict__ pcd = peers.cd[o];
         const BhCellS* __restrict__ psk = peers.sk[o];
         const int rp = (int)table[c].pos;
-        for (int j = 1 + lane; j < B; j += 32) bh_let_place(let, bh_let_wire(pcd, psk, rp + j, rp), d, j, half);
+        for (int j = j0 + lane; j < j1; j += 32) bh_let_place(let, bh_let_wire(pcd, psk, rp + j, rp), d, j, half);
     } else {
         const BhLetWire* in = recvbuf + recvoff[c];
-        for (int j = 1 + lane; j < B; j += 32) bh_let_place(let, in[j - 1], d, j, half);
+        for (int j = j0 + lane; j < j1; j += 32) bh_let_place(let, in[j - 1], d, j, half);
     }
 }
 
@@ -339,7 +389,7 @@ k_let_climb(BhTreeView let, BhRoot root, BhLetItems it, const BhLetEntry* __rest
 __global__ void __launch_bounds__(256)
 k_let_leafpos(int n_own, const int* __restrict__ lleaf, const double* __restrict__ lx, const double* __restrict__ ly,
               BhRoot root, BhGrid grid, int ell, const BhLetEntry* __restrict__ table, const int* __restrict__ dst,
-              const int* __restrict__ blk, BhTreeView let, int* __restrict__ leafpos) {
+              const int* __restrict__ blk, BhTreeView let, int* __restrict__ leafpos, int* __restrict__ dcnt) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31;
     const bool live = j < n_own;
@@ -355,19 +405,47 @@ k_let_leafpos(int n_own, const int* __restrict__ lleaf, const double* __restrict
         else if (table[c].count == 1.0) out = d;                 // the stray is the only body of its code
         else { B = blk[c]; search = B > 1; }
     }
-    // strays (rare): the whole warp scans the imported block for the leaf with the stray's exact coordinates
-    unsigned todo = __ballot_sync(0xffffffffu, search);
-    while (todo) {
-        const int src = __ffs(todo) - 1;
-        todo &= todo - 1;
-        const int sd = __shfl_sync(0xffffffffu, d, src), sB = __shfl_sync(0xffffffffu, B, src);
-        const double sx = __shfl_sync(0xffffffffu, px, src), sy = __shfl_sync(0xffffffffu, py, src);
-        int found = 0x7fffffff;
-        for (int q = sd + 1 + lane; q < sd + sB; q += 32)
-            if (let.sk[q].skip == q + 1 && let.cd[q].comx == sx && let.cd[q].comy == sy) { found = q; break; }
+    // strays: the leaf with the stray's exact coordinates sits in the block its host rank built.  Descend the block by
+    // the digits of the stray's key: all children of a cell are one level below it, and the child on the path is the
+    // one whose own centre of mass (inside its box) has the wanted digit.  The centre of mass of a deep cell of a
+    // dense core can round onto (or past) a box edge and name no child or the wrong one: then the leaf test at the
+    // end fails, and the warp scans the subtree of the cell three levels above the point of failure — and only if
+    // that fails too the whole block (a level-ELL code of a galactic core holds 10^5 cells: scanning it by default
+    // cost 17 ms per evaluation at 100M bodies, for 21 strays).
+    const int d_block = d, B_block = B;
+    if (search) {
+        atomicAdd(&dcnt[LET_D_DESCENTS], 1);
+        const uint64_t key = grid.exact ? bh_morton_key_grid(grid, root.levels, px, py) : bh_morton_key(root, px, py);
+        int q = d, qa1 = d, qa2 = d, qa3 = d;      // the last three cells of the path above q
+        bool ok = true;
+        while (ok && let.sk[q].skip != q + 1) {
+            const BhCellS sq = let.sk[q];
+            int next = -1;
+            for (int ch = q + 1; ch < sq.skip; ch = let.sk[ch].skip) {
+                const BhCellD cc = let.cd[ch];
+                const uint64_t kc = grid.exact ? bh_morton_key_grid(grid, root.levels, cc.comx, cc.comy) : bh_morton_key(root, cc.comx, cc.comy);
+                if (((kc ^ key) >> (2 * (root.levels - sq.level - 1))) == 0) { next = ch; break; }   // shares level + 1 digits
+            }
+            if (next < 0) ok = false; else { qa3 = qa2; qa2 = qa1; qa1 = q; q = next; }
+        }
+        if (ok && q > d && let.cd[q].comx == px && let.cd[q].comy == py) { out = q; search = false; }
+        else { atomicAdd(&dcnt[LET_D_SCANS], 1); d = qa3; B = let.sk[qa3].skip - qa3; }
+    }
+    for (int stage = 0; stage < 2; ++stage) {
+        unsigned todo = __ballot_sync(0xffffffffu, search);
+        while (todo) {
+            const int src = __ffs(todo) - 1;
+            todo &= todo - 1;
+            const int sd = __shfl_sync(0xffffffffu, d, src), sB = __shfl_sync(0xffffffffu, B, src);
+            const double sx = __shfl_sync(0xffffffffu, px, src), sy = __shfl_sync(0xffffffffu, py, src);
+            int found = 0x7fffffff;
+            for (int q = sd + 1 + lane; q < sd + sB; q += 32)
+                if (let.sk[q].skip == q + 1 && let.cd[q].comx == sx && let.cd[q].comy == sy) { found = q; break; }
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) found = min(found, __shfl_xor_sync(0xffffffffu, found, o));
-        if (lane == src && found != 0x7fffffff) out = found;
+            for (int o = 16; o > 0; o >>= 1) found = min(found, __shfl_xor_sync(0xffffffffu, found, o));
+            if (lane == src && found != 0x7fffffff) { out = found; search = false; }
+        }
+        d = d_block; B = B_block;                  // second stage: whatever is still missing, in the whole block
     }
     if (live) leafpos[j] = out;
 }
@@ -426,6 +504,9 @@ struct bh_let_state {
     // local source arrays: own slice, then guests
     double *lx = nullptr, *ly = nullptr, *lm = nullptr;
     int *lperm = nullptr, *lleaf = nullptr;
+    int *nchunk = nullptr, *chunkoff = nullptr; int64_t nchunk_cap = 0, chunkoff_cap = 0;   // k_let_blocks work list
+    int *gsrc = nullptr, *stray_slot = nullptr;        // guest -> (rank, segment entry); own segment entry -> own body
+    int64_t gsrc_cap = 0, stray_slot_cap = 0;
     int64_t lx_cap = 0, ly_cap = 0, lm_cap = 0, lperm_cap = 0, lleaf_cap = 0;
     double* segs = nullptr; int64_t segs_cap = 0;
     BhLetEntry* table = nullptr; int64_t table_cap = 0;
@@ -456,6 +537,9 @@ struct bh_let_state {
     LetPeers peers{};
     // statistics of the last LET evaluation
     int64_t last_imported = 0, last_sent = 0, last_strays = 0, last_guests_max = 0, evaluations = 0, fallbacks = 0;
+    bool returns_applied = false;   // the last evaluation changed positions of own strays (sent back by their host ranks)
+    int64_t jret_total = 0;        // guest positions this rank sent back to their home ranks after a jitter replay
+    int64_t fb_jitter = 0, fb_strays = 0, fb_cells = 0;   // fallbacks by reason (a fallback may have several)
     // phase timers of let_evaluate (CUDA events, folded at the start of the next evaluation)
     static constexpr int NPH = 14;
     cudaEvent_t pe[NPH + 1] = {};
@@ -466,7 +550,7 @@ struct bh_let_state {
     double cpu_t[NPH + 1] = {0};
 
     void release() {
-        void* ptrs[] = {lx, ly, lm, lperm, lleaf, segs, table, nit, blk, recvsz, recvoff, item_first, dst, sendsz, sendoff, ikey,
+        void* ptrs[] = {nchunk, chunkoff, gsrc, stray_slot, lx, ly, lm, lperm, lleaf, segs, table, nit, blk, recvsz, recvoff, item_first, dst, sendsz, sendoff, ikey,
                         itype, iw, icnt, iS, iW, ilp, sendbuf, recvbuf, cell, cd, sk, arrived, dcnt, dcollect};
         for (void* p : ptrs) if (p) cudaFree(p);
         if (hcollect) cudaFreeHost(hcollect);

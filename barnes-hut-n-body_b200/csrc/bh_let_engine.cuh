@@ -155,15 +155,17 @@ inline int bh_engine::let_evaluate(int slot) {
     LET_PHASE(0);
 
     // ---- 1. local arrays, footprint, strays
+    BH_RC(wait_inputs());            // bh_step_io_slice: the slice's masses may still be in flight on the copy stream
     const int64_t nl_max = (int64_t)n_own + (int64_t)(P - 1) * cap;
     LET_GROW(lx, nl_max + PAD); LET_GROW(ly, nl_max + PAD); LET_GROW(lm, nl_max + PAD);
     LET_GROW(lperm, nl_max + PAD); LET_GROW(lleaf, nl_max + PAD);
+    LET_GROW(gsrc, (int64_t)(P - 1) * cap + 1); LET_GROW(stray_slot, (int64_t)cap + 1);
     LET_GROW(segs, let.seg_len * P);
     double* myseg = let.segs + (size_t)rank * let.seg_len;
     k_let_seg_init<<<grid_for(LET_SEG_HDR + let.bw, 256), 256, 0, st>>>(myseg, let.bw, let.dcnt);
     if (n_own > 0)
         k_let_local<<<grid_for(n_own, 256), 256, 0, st>>>(n_own, x + lo, y + lo, m + lo, perm + lo, root, grid, ell, let.lam, c_lo, c_hi,
-                                                            cap, let.lx, let.ly, let.lm, let.lperm, myseg, let.bw, let.dcnt);
+                                                            cap, let.lx, let.ly, let.lm, let.lperm, myseg, let.bw, let.dcnt, let.stray_slot);
     k_let_seg_header<<<1, 1, 0, st>>>(myseg, let.dcnt, cap);
     ctr.kernel_launches += 3;
     LET_PHASE(1);   // 0: own slice -> local arrays, footprint, strays
@@ -178,7 +180,7 @@ inline int bh_engine::let_evaluate(int slot) {
     BH_TRY(cudaMemsetAsync(let.lm + n_own, 0, (size_t)others * sizeof(double), st));
     BH_TRY(cudaMemsetAsync(let.lperm + n_own, 0, (size_t)others * sizeof(int), st));
     k_let_guests<<<grid_for((int64_t)P * cap, 256), 256, 0, st>>>(let.segs, let.seg_len, let.bw, cap, P, rank, root, grid, ell, c_lo, c_hi,
-                                                                   n_own, (int)others, let.lx, let.ly, let.lm, let.lperm, let.dcnt);
+                                                                   n_own, (int)others, let.lx, let.ly, let.lm, let.lperm, let.dcnt, let.gsrc);
     ctr.kernel_launches += 1;
     LET_PHASE(3);   // 2: guests
     // ---- 3. the single-GPU build on the local arrays (keys outside [c_lo, c_hi) -> not in the tree)
@@ -197,21 +199,24 @@ inline int bh_engine::let_evaluate(int slot) {
     LET_PHASE(4);   // 3: local build
     tree_valid = false;              // the engine's cell arrays hold the LOCAL tree: exports rebuild the global one
     const bool jit = jitter_active;
-    if (let.local_overflow) BH_TRY(cudaMemsetAsync(let.dcnt + LET_D_FLAG, 0x01, sizeof(int), st));   // -> retry flag of this rank
+    if (let.local_overflow) BH_TRY(cudaMemsetAsync(let.dcnt + LET_D_FLAG, 0x04, sizeof(int), st));   // -> retry flag of this rank (reason 4)
+    // ---- 4. level-ELL summaries -> replicated table (P extra entries carry the ranks' retry flags, P x LET_JRET more the
+    //         positions of guests that a jitter replay on their host rank mutated)
+    const size_t table_entries = (size_t)ncodes + P + (size_t)P * LET_JRET;
+    LET_GROW(table, (int64_t)table_entries + 1);
+    BH_TRY(cudaMemsetAsync(let.table, 0, table_entries * sizeof(BhLetEntry), st));
     if (jit && n_in > 0) {
-        k_let_jitter_check<<<grid_for(n_in, 256), 256, 0, st>>>(keys_sorted, order, n_in, n_own, let.dcnt + LET_D_FLAG);
+        k_let_jitter_returns<<<grid_for(n_in, 256), 256, 0, st>>>(keys_sorted, order, n_in, n_own, let.lx, let.ly, let.gsrc, cap,
+                                                                    let.table + ncodes + P + (size_t)rank * LET_JRET, let.dcnt);
         ctr.kernel_launches += 1;
     }
-    // ---- 4. level-ELL summaries -> replicated table (the P extra entries carry the ranks' retry flags)
-    LET_GROW(table, ncodes + 17);
-    BH_TRY(cudaMemsetAsync(let.table, 0, (size_t)(ncodes + P) * sizeof(BhLetEntry), st));
     if (n_in > 0) {
         k_let_summary<<<grid_for(n_in, 256), 256, 0, st>>>(view(), root.levels, ell, let.lx, let.ly, let.lm, jit ? jflag : nullptr, let.table);
         ctr.kernel_launches += 1;
     }
     k_let_flag<<<1, 1, 0, st>>>(let.table + ncodes + rank, let.dcnt + LET_D_FLAG, let.segs, let.seg_len, P);
     LET_PHASE(5);   // 4: summaries
-    rc = A.AllReduce(let.table, let.table, (size_t)(ncodes + P) * 6, bhcomm::kFloat64, bhcomm::kSum, comm, st);
+    rc = A.AllReduce(let.table, let.table, table_entries * 6, bhcomm::kFloat64, bhcomm::kSum, comm, st);
     if (rc != bhcomm::kSuccess) return nccl_fail(rc, "ncclAllReduce(table)");
     LET_PHASE(6);   // 5: table all-reduce
     // ---- 5. plan
@@ -249,7 +254,8 @@ inline int bh_engine::let_evaluate(int slot) {
         BH_RC(excl_scan(let.icnt, n_slots, let.iS));
         BH_RC(excl_scan(let.iw, n_slots, let.iW));
     }
-    k_let_collect<<<1, 32, 0, st>>>(let.item_first, ncodes, let.iS, let.iW, let.recvoff, let.sendoff, let.split, let.dcnt, let.dcollect);
+    k_let_collect<<<1, 32, 0, st>>>(let.item_first, ncodes, let.iS, let.iW, let.recvoff, let.sendoff, let.split, let.dcnt, let.dcollect,
+                                let.table + ncodes + P);
     ctr.kernel_launches += 5;
     BH_TRY(cudaMemcpyAsync(let.hcollect, let.dcollect, 40 * sizeof(int), cudaMemcpyDeviceToHost, st));
     BH_TRY(cudaMemcpy2DAsync(let.hhdr, sizeof(double), let.table + ncodes, sizeof(BhLetEntry), sizeof(double), (size_t)P,
@@ -258,8 +264,17 @@ inline int bh_engine::let_evaluate(int slot) {
     BH_TRY(cudaGetLastError());
     LET_PHASE(7);   // 6: plan + scans + host sync
     // a stray sits in a jitter cluster of its host, or a rank had more strays than its segment holds
-    for (int q = 0; q < P; ++q) if (let.hhdr[q] != 0.0) return BH_LET_RETRY;
+    {
+        int why = 0;
+        for (int q = 0; q < P; ++q) why |= (int)let.hhdr[q];
+        if (why) {
+            let.fb_jitter += (why & 1) != 0; let.fb_strays += (why & 2) != 0; let.fb_cells += (why & 4) != 0;
+            return BH_LET_RETRY;
+        }
+    }
     let.last_strays = let.hcollect[38];
+    let.jret_total += let.hcollect[36];
+    let.returns_applied = let.hcollect[37] > 0;
     let.n_items = let.hcollect[0];
     let.M = let.hcollect[1];
     const int* roff = let.hcollect + 2;
@@ -268,6 +283,11 @@ inline int bh_engine::let_evaluate(int slot) {
         BH_TRY(cudaMemcpyAsync(x + lo, let.lx, (size_t)n_own * sizeof(double), cudaMemcpyDeviceToDevice, st));
         BH_TRY(cudaMemcpyAsync(y + lo, let.ly, (size_t)n_own * sizeof(double), cudaMemcpyDeviceToDevice, st));
         let.pos_valid = false;
+    }
+    if (n_own > 0) {                 // ... and the mutation of own strays by the replay on THEIR host ranks
+        k_let_apply_returns<<<grid_for((int64_t)P * LET_JRET, 256), 256, 0, st>>>(let.table + ncodes + P, P * LET_JRET, rank, let.stray_slot,
+                                                                                 x + lo, y + lo, let.lx, let.ly);
+        ctr.kernel_launches += 1;
     }
     // ---- 6. blocks to the ranks that may open them
     LET_GROW(cell, (int64_t)let.M + 1); LET_GROW(cd, (int64_t)let.M + 1); LET_GROW(sk, (int64_t)let.M + 1); LET_GROW(arrived, (int64_t)let.M + 1);
@@ -297,14 +317,21 @@ inline int bh_engine::let_evaluate(int slot) {
     if (let.n_items > 0) {
         k_let_emit<<<grid_for(let.n_items, 256), 256, 0, st>>>(it, let.sk, let.arrived, root.levels, ell, let.ilp, let.dst);
         LET_PHASE(9);    // 8: top-tree skeletons
-        k_let_blocks<<<grid_for((int64_t)ncodes * 32, 256), 256, 0, st>>>(lv, let.table, ncodes, let.split, let.nit, let.blk, let.dst, let.recvoff,
-                                                                          let.recvbuf, cd, sk, root.half, let.peers, let.ipc_ok ? 1 : 0);
+        // one warp per chunk of LET_BLK_CHUNK cells: chunk counts per code, their exclusive scan, then at most
+        // M / chunk + ncodes warps (the kernel reads the real total from the scan)
+        LET_GROW(nchunk, (int64_t)ncodes + 1); LET_GROW(chunkoff, (int64_t)ncodes + 2);
+        k_let_block_chunks<<<grid_for(ncodes, 256), 256, 0, st>>>(let.nit, let.blk, ncodes, let.nchunk);
+        BH_RC(excl_scan(let.nchunk, (int)ncodes, let.chunkoff));
+        const int64_t max_chunks = (int64_t)let.M / LET_BLK_CHUNK + (int64_t)ncodes + 1;
+        k_let_blocks<<<grid_for(max_chunks * 32, 256), 256, 0, st>>>(lv, let.table, ncodes, let.split, let.chunkoff, let.blk, let.dst, let.recvoff,
+                                                                     let.recvbuf, cd, sk, root.half, let.peers, let.ipc_ok ? 1 : 0);
+        ctr.kernel_launches += 1;
     } else LET_PHASE(9);
     LET_PHASE(10);   // 9: own + imported blocks
     k_let_climb<<<std::max(1, grid_for(let.n_items, 128)), 128, 0, st>>>(lv, root, it, let.table, root.levels, ell, let.ilp);
     LET_PHASE(11);   // 10: top-tree climb
     if (n_own > 0)
-        k_let_leafpos<<<grid_for(n_own, 256), 256, 0, st>>>(n_own, let.lleaf, let.lx, let.ly, root, grid, ell, let.table, let.dst, let.blk, lv, leafpos + lo);
+        k_let_leafpos<<<grid_for(n_own, 256), 256, 0, st>>>(n_own, let.lleaf, let.lx, let.ly, root, grid, ell, let.table, let.dst, let.blk, lv, leafpos + lo, let.dcnt);
     ctr.kernel_launches += 4;
     LET_PHASE(12);   // 11: leaf positions
     LET_PHASE(13); LET_PHASE(14);

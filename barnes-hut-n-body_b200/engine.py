@@ -117,6 +117,32 @@ class NativeEngine:
         self._check(self.lib.bh_get_bodies(self._h, n, *[_dp(a) for a in arrs], C.byref(n_out)), "bh_get_bodies")
         return arrs
 
+    def slice_index(self) -> np.ndarray:
+        """Positions in the `bodies` list of the bodies of this rank's slice, in home order (bh_get_slice_index)."""
+        n = self.n
+        ui = np.empty(n, np.int32)
+        k = C.c_int64()
+        self._check(self.lib.bh_get_slice_index(self._h, n, _ip(ui), C.byref(k)), "bh_get_slice_index")
+        return ui[:k.value].copy()
+
+    def slice_epoch(self) -> int:
+        return int(self.lib.bh_slice_epoch(self._h))
+
+    def step_io_slice(self, nsteps: int = 1, inputs=None, out=None) -> int:
+        """[this rank's slice in] ; nsteps x step() ; [slice out] — every rank moves only its own bodies
+        (bh_step_io_slice).  `inputs` / `out`: 5 float64 arrays in slice order; returns the slice length after the steps."""
+        ins, n_in = [None] * 5, 0
+        if inputs is not None:
+            ins = [_dp(a) for a in inputs]
+            n_in = len(inputs[0])
+        outs, cap = [None] * 5, 0
+        if out is not None:
+            outs = [_dp(a) for a in out]
+            cap = len(out[0])
+        k = C.c_int64()
+        self._check(self.lib.bh_step_io_slice(self._h, nsteps, n_in, *ins, cap, *outs, C.byref(k)), "bh_step_io_slice")
+        return int(k.value)
+
     def evaluate_slice(self):
         """One evaluation of this rank's slice in the engine's current multi-GPU mode: (ax, ay, user_index)."""
         n = self.n
@@ -289,7 +315,8 @@ class NativeEngine:
         self._check(self.lib.bh_get_let_stats(self._h, v.ctypes.data_as(C.POINTER(C.c_int64)), 26), "bh_get_let_stats")
         # [0] 0 = off, 1 = on (blocks over ncclSend/ncclRecv), 2 = on (blocks over NVLink peer memory)
         names = ("enabled", "partition_valid", "cut_level", "let_evaluations", "fallbacks", "let_cells", "cells_imported",
-                 "cells_sent", "own_strays", "top_items")
+                 "cells_sent", "own_strays", "top_items", "fallbacks_guest_in_jitter_cluster", "fallbacks_stray_overflow",
+                 "fallbacks_cell_overflow", "stray_capacity", "jitter_positions_returned", "stray_leaf_descents", "stray_leaf_scans")
         return {k: int(x) for k, x in zip(names, v)}
 
     # -- multi-GPU --------------------------------------------------------------------

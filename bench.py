@@ -174,7 +174,7 @@ def build_config_scene(eng, name):
     """Appends the bodies of config `name` with the device generators (bh_append_disk: BodyFactory.makeGalaxyDisk
     laws, counter-based RNG keyed by the seed, so every rank generates the same list) and returns (W, H, label)."""
     def disk(n, x, y, r, vx=0.0, vy=0.0, central=50_000.0, sat=5_000.0, seed=1):
-        p = eng.default_disk_params(2400, 800, x=x, y=y, r=r, vx=vx, vy=vy, central_mass=central, total_satellite_mass=sat)
+        p = eng.disk_params(2400, 800, x=x, y=y, r=r, vx=vx, vy=vy, central_mass=central, total_satellite_mass=sat)
         eng.append_disk(n, p, seed=seed)
     if name == "C3":      # 10M two-disk merger with central black holes: the reference scene (NBodyPanel.kt:83-99) x 800 bodies
         W = H = 32768
@@ -255,7 +255,9 @@ def run_config(name, steps, warm, local_rank, rank, world, dist, allmax, allsum,
         if world > 1:
             ls = eng.let_stats()
             rec["mode"] = "domain (LET)" if ls["let_evaluations"] > 0 else "replicated tree"
-            rec["domain_mode_rank0"] = {k: ls[k] for k in ("let_evaluations", "fallbacks", "let_cells", "cells_imported", "own_strays")}
+            rec["domain_mode_rank0"] = {k: ls[k] for k in ("let_evaluations", "fallbacks", "fallbacks_guest_in_jitter_cluster", "fallbacks_stray_overflow",
+                                                           "fallbacks_cell_overflow", "stray_capacity", "let_cells", "cells_imported", "own_strays", "jitter_positions_returned",
+                                                           "stray_leaf_descents", "stray_leaf_scans")}
         return rec
     finally:
         eng.close()
@@ -428,36 +430,76 @@ def main():
                       "algorithmic_bytes_per_body": bytes_per_body}
 
     # ---- end to end through the C ABI with HOST buffers --------------------------------------
-    host = [torch.from_numpy(np.ascontiguousarray(a)).pin_memory() for a in scene]
-    hnp = [t.numpy() for t in host]
-    out = [torch.empty(n, dtype=torch.float64).pin_memory() for _ in range(5)]
-    onp = tuple(t.numpy() for t in out)
     e2e_steps = max(3, min(args.steps, 10))
-    eng.step_io(1, inputs=hnp, out=onp)
-    eng.reset_counters()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        # resetBodies(host arrays) + step() + getBodies(host arrays) in ONE C-ABI call: H2D of this
-        # step's inputs and D2H of its result are inside the call (and inside the timed region),
-        # overlapped with the compute where the data dependences allow (bh_step_io)
+    if world == 1:
+        host = [torch.from_numpy(np.ascontiguousarray(a)).pin_memory() for a in scene]
+        hnp = [t.numpy() for t in host]
+        out = [torch.empty(n, dtype=torch.float64).pin_memory() for _ in range(5)]
+        onp = tuple(t.numpy() for t in out)
         eng.step_io(1, inputs=hnp, out=onp)
-    barrier()
-    e2e_wall = allmax(time.perf_counter() - t0)
-    e2e_inter = allsum(float(eng.counters()["total_interactions"]))
-    # the same three calls made separately (no overlap), for comparison
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        eng.set_bodies(*hnp)
-        eng.step(1)
-        eng.get_bodies(out=onp)
-    barrier()
-    seq_wall = allmax(time.perf_counter() - t0)
-    e2e = {"value": e2e_inter / e2e_wall, "unit": "interactions/s", "steps_per_s": e2e_steps / e2e_wall,
-           "h2d_bytes_per_step": 5 * 8 * n, "d2h_bytes_per_step": 5 * 8 * n, "steps": e2e_steps,
-           "api": "bh_step_io(1, host in, host out) per step: resetBodies + step + getBodies, pinned host arrays, copies overlapped with compute",
-           "steps_per_s_separate_calls": e2e_steps / seq_wall}
+        eng.reset_counters()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            # resetBodies(host arrays) + step() + getBodies(host arrays) in ONE C-ABI call: H2D of this
+            # step's inputs and D2H of its result are inside the call (and inside the timed region),
+            # overlapped with the compute where the data dependences allow (bh_step_io)
+            eng.step_io(1, inputs=hnp, out=onp)
+        barrier()
+        e2e_wall = allmax(time.perf_counter() - t0)
+        e2e_inter = allsum(float(eng.counters()["total_interactions"]))
+        # the same three calls made separately (no overlap), for comparison
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            eng.set_bodies(*hnp)
+            eng.step(1)
+            eng.get_bodies(out=onp)
+        barrier()
+        seq_wall = allmax(time.perf_counter() - t0)
+        e2e = {"value": e2e_inter / e2e_wall, "unit": "interactions/s", "steps_per_s": e2e_steps / e2e_wall,
+               "h2d_bytes_per_step": 5 * 8 * n, "d2h_bytes_per_step": 5 * 8 * n, "steps": e2e_steps,
+               "api": "bh_step_io(1, host in, host out) per step: resetBodies + step + getBodies, pinned host arrays, copies overlapped with compute",
+               "steps_per_s_separate_calls": e2e_steps / seq_wall}
+    else:
+        # N > 1: SHARDED I/O — every rank moves only the bodies of its own slice (bh_step_io_slice): the slice's state goes
+        # up from pinned host memory, one step runs, the slice's new state comes down; when a re-homing re-cut the
+        # slices (bh_slice_epoch) the rank fetches the new index and re-gathers its host arrays, inside the timed region
+        torch.set_num_threads(max(1, min(16, (os.cpu_count() or 1) // world)))   # (torchrun pins OMP_NUM_THREADS to 1)
+        full = [torch.from_numpy(a) for a in eng.get_bodies()]            # state after the device-resident steps
+        hs_t = [torch.empty(n, dtype=torch.float64).pin_memory() for _ in range(5)]
+        hslice = [t.numpy() for t in hs_t]
+        oslice = [torch.empty(n, dtype=torch.float64).pin_memory().numpy() for _ in range(5)]
+
+        def regather():
+            idx = torch.from_numpy(eng.slice_index().astype(np.int64))
+            for dst, src in zip(hs_t, full):
+                torch.index_select(src, 0, idx, out=dst[:len(idx)])
+            return len(idx), eng.slice_epoch()
+
+        k, epoch = regather()
+        eng.step_io_slice(1, inputs=[a[:k] for a in hslice], out=oslice)
+        k, epoch = regather()
+        eng.reset_counters()
+        h2d = d2h = 0
+        regathers = 0
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            if eng.slice_epoch() != epoch:
+                k, epoch = regather()
+                regathers += 1
+            k_out = eng.step_io_slice(1, inputs=[a[:k] for a in hslice], out=oslice)
+            h2d += 5 * 8 * k
+            d2h += 5 * 8 * k_out
+        barrier()
+        e2e_wall = allmax(time.perf_counter() - t0)
+        e2e_inter = allsum(float(eng.counters()["total_interactions"]))
+        e2e = {"value": e2e_inter / e2e_wall, "unit": "interactions/s", "steps_per_s": e2e_steps / e2e_wall,
+               "h2d_bytes_per_step": allsum(float(h2d)) / e2e_steps, "d2h_bytes_per_step": allsum(float(d2h)) / e2e_steps, "steps": e2e_steps,
+               "api": "bh_step_io_slice(1, slice in, slice out) per step on every rank: only the rank's own bodies cross PCIe (pinned host arrays); "
+                      "slice index re-fetched and host arrays re-gathered when a re-homing re-cut the slices",
+               "slice_regathers_in_timed_region": regathers}
 
     # ---- N > 1: the run checks itself (domain mode vs replicated tree vs one rank walking every body) -----------
     pcheck = None

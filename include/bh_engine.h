@@ -315,6 +315,23 @@ int bh_export_slice(bh_engine* e, int32_t field, int64_t cap, double* a, double*
 /* the concatenation of every rank's exported slice (n = bh_num_bodies doubles each) */
 int bh_import_slices(bh_engine* e, int32_t field, int64_t n, const double* a, const double* b);
 
+/* Sharded end-to-end I/O: every rank moves ONLY ITS OWN SLICE between host and device.  The slice is the set of
+ * bodies this rank walks and integrates, in the engine's home order; bh_get_slice_index names them (positions in
+ * the `bodies` list) as the device holds them at the time of the call, and bh_slice_epoch changes whenever the
+ * slices were re-cut or re-ordered (re-homing: bodies migrate between ranks), i.e. whenever the index has to be
+ * fetched again: arrays that come out of a call are in the order the index shows AFTER that call.
+ *   bh_step_io_slice: [slice state in: x, y, vx, vy, m of the slice, home order; NULL = keep] ; nsteps x step() ;
+ *   [slice state out].  The rest of the state is exchanged between the ranks by the engine as the mode needs it
+ *   (nothing in domain mode; positions / masses / velocities of the other slices before a replicated build).
+ * With one rank the slice is the whole list (in home order).  Refused while the merge rule is enabled on more than
+ * one rank (removals re-index the list on every rank). */
+int bh_get_slice_index(bh_engine* e, int64_t cap, int32_t* user_index, int64_t* n_slice);
+int64_t bh_slice_epoch(const bh_engine* e);
+int bh_step_io_slice(bh_engine* e, int32_t nsteps, int64_t n_in,
+                     const double* x_in, const double* y_in, const double* vx_in, const double* vy_in, const double* m_in,
+                     int64_t cap_out, double* x_out, double* y_out, double* vx_out, double* vy_out, double* m_out,
+                     int64_t* n_out);
+
 /* One force evaluation (buildTree + computeAccelerations, BarnesHutAlg.kt:359-366 + :374-395) of THIS RANK'S
  * slice of targets, in the multi-GPU mode the engine is in (domain mode / replicated tree), without
  * integrating: ax/ay[k] for the k-th body of the slice, user_index[k] = its position in the `bodies` list.

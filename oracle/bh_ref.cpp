@@ -825,6 +825,24 @@ int bh_import_slices(bh_engine* e, int32_t field, int64_t n, const double* a, co
     if (field == BH_FIELD_POS) e->lastTree = nullptr;
     return BH_OK;
 }
+int bh_get_slice_index(bh_engine* e, int64_t cap, int32_t* user_index, int64_t* n_slice) {
+    if (!e) return BH_E_ARG;
+    int64_t lo, hi;
+    e->mySlice(&lo, &hi);
+    if (n_slice) *n_slice = hi - lo;
+    if (cap < hi - lo) return fail(e, BH_E_ARG, "bh_get_slice_index: capacity too small");
+    if (user_index) for (int64_t k = lo; k < hi; ++k) user_index[k - lo] = (int32_t)k;   // the port keeps list order
+    return BH_OK;
+}
+int64_t bh_slice_epoch(const bh_engine*) { return 0; }
+int bh_step_io_slice(bh_engine* e, int32_t nsteps, int64_t n_in, const double* x_in, const double* y_in, const double* vx_in,
+                     const double* vy_in, const double* m_in, int64_t cap_out, double* x_out, double* y_out, double* vx_out,
+                     double* vy_out, double* m_out, int64_t* n_out) {
+    if (!e) return BH_E_ARG;
+    if (e->world > 1) return fail(e, BH_E_UNSUPPORTED, "bh_step_io_slice: the reference port is single-process here (its slice is the whole list)");
+    return bh_step_io(e, nsteps, n_in, x_in, y_in, vx_in, vy_in, m_in, cap_out, x_out, y_out, vx_out, vy_out, m_out, n_out);
+}
+
 int bh_evaluate_slice(bh_engine* e, int64_t cap, double* ax, double* ay, int32_t* user_index, int64_t* n_slice) {
     if (!e) return BH_E_ARG;
     int64_t lo, hi;

@@ -117,7 +117,7 @@ def test_cuda_host_staged_world2_is_bit_identical_to_one_gpu(cuda_lib, tmp_path,
 @pytest.mark.parametrize("merge", [0, 1], ids=["merge-off", "merge-on"])
 def test_cuda_nccl_is_bit_identical_to_one_gpu(cuda_lib, tmp_path, merge):
     import torch
-    world = min(torch.cuda.device_count(), 4)
+    world = min(torch.cuda.device_count(), 8)
     if world < 2:
         pytest.skip("needs >= 2 GPUs (run with gpurun --gpus 2)")
     scene, path = _scene_file(tmp_path, merge)
@@ -126,7 +126,28 @@ def test_cuda_nccl_is_bit_identical_to_one_gpu(cuda_lib, tmp_path, merge):
     _assert_identical(ranks, single, origin, ctr)
 
 
+def _jitter_stray_scene():
+    """Two disks + 2000 PAIRS of bodies 2e-4 px apart (they share a depth-21 cell: the jitter regime of BH.kt:145-156
+    mutates them in every build) that fly at 400 px/t across the code boundaries of the partition, so that pairs become
+    strays of their home rank and guests — inside a jitter cluster — of the rank that hosts their cell."""
+    s = [a.copy() for a in scenes.snap_f32(scenes.default_two_disks(n1=32000, n2=8000, seed=35))]
+    rng = np.random.default_rng(36)
+    k = 2000
+    half = 1202.0
+    w = 2.0 * half / 16.0                                  # side of a level-4 cell (the coarsest cut)
+    col = rng.integers(2, 14, k)
+    bx = -2.0 + col * w - rng.uniform(0.5, 6.0, k)         # just left of a cell boundary, moving right
+    by = rng.uniform(-300.0, 1100.0, k)
+    for j in range(k):
+        for t in range(2):
+            i = 1000 + 2 * j + t                              # (satellites of the first disk are replaced)
+            s[0][i], s[1][i] = np.float32(bx[j]) + t * 2.0e-4, np.float32(by[j])
+            s[2][i], s[3][i] = 400.0, 0.0
+    return tuple(np.ascontiguousarray(a) for a in s)
+
+
 LET_CASES = [
+    ("jitter clusters that cross rank boundaries (positions sent back to the home rank)", _jitter_stray_scene, 0.5, 9, 4),
     ("two-disk 40k", lambda: scenes.snap_f32(scenes.default_two_disks(n1=32000, n2=8000, seed=31)), 0.5, 9, 3),
     ("two-disk 40k, stray overflow -> fallback", lambda: scenes.snap_f32(scenes.default_two_disks(n1=32000, n2=8000, seed=31)), 0.5, 9, 4),
     ("cloud 100k θ0.8", lambda: scenes.snap_f32(scenes.make_uniform_random(100_000, 0.5, seed=32)), 0.8, 6, 2),
@@ -143,7 +164,7 @@ def test_cuda_domain_mode_is_bit_identical_to_one_gpu(cuda_lib, tmp_path, name, 
     builds, LET evaluations with strays in between — bit-identical to one GPU; interaction and
     opened-cell totals equal."""
     import torch
-    world = min(torch.cuda.device_count(), 4)
+    world = min(torch.cuda.device_count(), 8)
     if world < 2:
         pytest.skip("needs >= 2 GPUs (run with gpurun --gpus 2)")
     scene = gen()
@@ -165,5 +186,10 @@ def test_cuda_domain_mode_is_bit_identical_to_one_gpu(cuda_lib, tmp_path, name, 
         st = dict(zip([str(s) for s in z["let_keys"]], [int(v) for v in z["let"]]))
         # enabled: 2 = blocks imported over NVLink peer memory (CUDA IPC), 1 = over ncclSend/ncclRecv
         assert st["enabled"] == (1 if "ncclSend" in name else 2) and st["let_evaluations"] > 0 and (st["fallbacks"] > 0) == overflow, st
+        if "jitter" in name:
+            assert st["fallbacks_guest_in_jitter_cluster"] == 0, st
+    if "jitter" in name:
+        returned = sum(dict(zip([str(s) for s in z["let_keys"]], [int(v) for v in z["let"]]))["jitter_positions_returned"] for z in ranks)
+        assert returned > 0, returned                      # guests inside jitter clusters did occur, and were sent back
     assert sum(int(z["interactions"]) for z in ranks) == ctr["total_interactions"]
     assert sum(int(z["opened"]) for z in ranks) == ctr["total_opened"]
