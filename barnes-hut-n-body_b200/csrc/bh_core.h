@@ -287,7 +287,17 @@ struct BhTreeView {
     int*     arrived;       // climb counters, zero before the climb         [M]
     int n_in;               // bodies in the tree
     int M;                  // cells = n_in + #internal
+    // Sync-free builds (small body counts: the cell arrays are sized for the worst case, so the host never reads
+    // the counts back): n_in and the number of internal cells are taken from device memory by every kernel.
+    const int* dev_n_in;    // nullptr: n_in / M above are valid
+    const int* dev_n_int;
 };
+// kernels call this first: with device-side counts it fills n_in / M of their (by-value) copy of the view
+#if defined(__CUDACC__)
+__device__ __forceinline__ void bh_view_resolve(BhTreeView& t) {
+    if (t.dev_n_in) { t.n_in = *t.dev_n_in; t.M = t.n_in + *t.dev_n_int; }
+}
+#endif
 
 #if defined(__CUDA_ARCH__)
 // acq_rel RMW: releases this thread's child record, acquires the siblings' records

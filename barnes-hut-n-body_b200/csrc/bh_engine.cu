@@ -67,7 +67,7 @@ struct bh_engine {
     // to read its timers.  Per slot: [0..3] evaluation A, [4..7] evaluation B, [8..9] step,
     // [12..13] exchange, [14..15] merge rule.  `ev` = the slot in use; call_ev = whole call.
     static constexpr int EV_RING = 4;
-    struct EvSlot { cudaEvent_t e[16]{}; bool used = false, has_comm = false, has_merge = false; };
+    struct EvSlot { cudaEvent_t e[16]{}; bool used = false, has_comm = false, has_merge = false, phases = true; };
     EvSlot ring[EV_RING];
     EvSlot* cur = &ring[0];
     cudaEvent_t* ev = ring[0].e;
@@ -115,6 +115,14 @@ struct bh_engine {
     int64_t climb_roots_cap = 0;
 
     bool tree_valid = false;
+    // sync-free builds + per-step CUDA graphs (small body counts, one GPU): see build() and run_steps()
+    static constexpr int64_t SYNCFREE_MAX_N = 262144;
+    bool syncfree_enabled = true;    // BH_SYNCFREE=0 switches both off
+    bool graph_enabled = true;       // BH_GRAPH=0: sync-free builds, but every kernel launched on its own
+    bool counts_on_host = true;      // n_in / M / jitter_active below describe the last build (false: still on the device)
+    bool capturing = false;          // the launches of the current step are being captured into a graph
+    cudaGraphExec_t gexec = nullptr;
+    int64_t ctr_graph_steps = 0, ctr_graph_instantiations = 0;
     BhRoot root{};
     int n_in = 0, n_internal = 0, M = 0;
     const uint64_t* keys_sorted = nullptr;
@@ -247,6 +255,7 @@ struct bh_engine {
         t.keys = keys_sorted; t.order = order; t.S = S;
         t.cell = cell; t.cd = cd; t.sk = sk; t.arrived = arrived;
         t.n_in = n_in; t.M = M;
+        if (!counts_on_host) { t.dev_n_in = &sc()->n_in; t.dev_n_int = &sc()->n_internal; }
         return t;
     }
 
@@ -352,7 +361,7 @@ struct bh_engine {
         const int nn = (int)n;
         if (!let.local_build) { BH_RC(sync_positions()); BH_RC(sync_masses()); }   // a replicated build needs every body's position and mass
         if (rehome_due && nn > 0) { BH_RC(sync_velocities()); BH_RC(wait_inputs()); }
-        if (timed) BH_TRY(cudaEventRecord(ev[slot + 0], st));
+        if (timed && !capturing) BH_TRY(cudaEventRecord(ev[slot + 0], st));
         bool rehomed = false;
         // zero: scalars | sort scratch (sized for this n) | scan status
         const int key_bits = 2 * root.levels + 1;   // +1: the not-in-tree sentinel 1<<2L sorts last
@@ -391,6 +400,34 @@ struct bh_engine {
             k_count_scan<<<grid_for(nn, SCAN_TILE), SCAN_THREADS, 0, st>>>(keys_sorted, root.levels, sc(), S, scan_status);
             ctr.kernel_launches += 1;
         }
+        if (syncfree_ok(nn)) {
+            // SYNC-FREE build (small body counts, one GPU): the cell arrays hold the worst case, so nothing has to be read
+            // back before the rest of the build is launched — n_in and the cell count stay on the device, every kernel
+            // takes them from there (BhTreeView::dev_n_in), and the launch shapes cover all n bodies.  The jitter replay
+            // is launched unconditionally (it returns at once when no two keys are equal).  No host round trip: the
+            // whole step can be captured into one CUDA graph (run_steps).
+            BH_RC(prepare_syncfree(nn, root.levels));      // (allocates only when n or the root box grew)
+            counts_on_host = false;
+            jitter_active = true;                          // unknown until finish(): handled as "maybe" (flags passed, no reuse)
+            acc_valid = false;
+            BH_TRY(cudaMemsetAsync(jflag, 0, (size_t)nn * sizeof(int), st));
+            k_jitter<<<grid_for(nn, 128), 128, 0, st>>>(keys_sorted, const_cast<int*>(order), -1, root, perm, x, y, jflag, sc());
+            BH_TRY(cudaMemsetAsync(leafpos, 0xFF, (size_t)nn * sizeof(int), st));   // -1: not in the tree
+            BH_TRY(cudaMemsetAsync(arrived, 0, (size_t)cell_cap * sizeof(int), st));
+            const BhTreeView t = view();
+            k_emit<<<grid_for(nn, 256), 256, 0, st>>>(t, root.levels);
+            BH_RC(wait_inputs());   // bh_step_io: the masses may still be in flight
+            int* n_roots = dflags + HF_N_ROOTS;
+            BH_TRY(cudaMemsetAsync(n_roots, 0, sizeof(int), st));
+            k_climb_block<<<grid_for(nn, CLIMB_B), CLIMB_B, 0, st>>>(t, root, x, y, m, jflag, leafpos, climb_roots, n_roots);
+            k_climb_top<<<std::min(grid_for(nn, 128 * 8), num_sms * 8), 128, 0, st>>>(t, root, climb_roots, n_roots);
+            ctr.kernel_launches += 4;
+            if (timed && !capturing) BH_TRY(cudaEventRecord(ev[slot + 1], st));
+            BH_TRY(cudaGetLastError());
+            tree_valid = true;
+            return BH_OK;
+        }
+        counts_on_host = true;
         BH_TRY(cudaMemcpyAsync(sc_host, sc(), sizeof(DevScalars), cudaMemcpyDeviceToHost, st));
         BH_TRY(cudaStreamSynchronize(st));
         BH_TRY(cudaGetLastError());
@@ -444,13 +481,26 @@ struct bh_engine {
                 ctr.kernel_launches += 3;
             }
         }
-        if (timed) BH_TRY(cudaEventRecord(ev[slot + 1], st));
+        if (timed && !capturing) BH_TRY(cudaEventRecord(ev[slot + 1], st));
         BH_TRY(cudaGetLastError());
         tree_valid = true;
         return BH_OK;
     }
     int64_t ctr_rehomes = 0, ctr_reused = 0;
     int io_steps_left = 0;
+    bool syncfree_ok(int64_t nn) const {
+        return syncfree_enabled && world == 1 && !let.local_build && nn > 0 && nn <= SYNCFREE_MAX_N && !(cfg.flags & BH_FLAG_REUSE_ACC);
+    }
+    // worst case of the cell count: every body adds at most `levels` internal cells on its path
+    int prepare_syncfree(int64_t nn, int levels) {
+        BH_RC(ensure_cells(nn * (levels + 1) + 2));
+        if (nn > climb_roots_cap) {
+            dev_free(climb_roots);
+            climb_roots_cap = std::max<int64_t>(nn + nn / 8, 1024);
+            BH_TRY(dev_alloc(&climb_roots, (size_t)climb_roots_cap));
+        }
+        return BH_OK;
+    }
     int walk_g = 0;                 // bodies per thread of the walk; 0 = automatic (BH_WALK_G=1|2 pins it)
     bool walk_affine = true;        // BH_WALK_AFFINE=0: every chunk from the global queue (no SM affinity)
     unsigned int* walk_queue = nullptr;   // work counters of the persistent walk kernel
@@ -484,7 +534,7 @@ struct bh_engine {
     // computeAccelerations(root), BH.kt:374-395, for the home slots [first, first+count)
     int walk(int64_t first, int64_t count, int slot = 0, const BhTreeView* over = nullptr) {
         const BhTreeView tv = over ? *over : view();
-        BH_TRY(cudaEventRecord(ev[slot + 2], st));
+        if (!capturing) BH_TRY(cudaEventRecord(ev[slot + 2], st));
         if (count > 0) {
             const BhWalkParams w = bh_walk_params(par.theta, par.soft2, par.root_half);
             // bodies per thread (bh_walk_multi): the widest group that still gives every SM >= 2 full waves of
@@ -514,7 +564,7 @@ struct bh_engine {
 #undef BH_LAUNCH_WALK
             ctr.kernel_launches += 1;
         }
-        BH_TRY(cudaEventRecord(ev[slot + 3], st));
+        if (!capturing) BH_TRY(cudaEventRecord(ev[slot + 3], st));
         BH_TRY(cudaGetLastError());
         return BH_OK;
     }
@@ -532,6 +582,16 @@ struct bh_engine {
         BH_TRY(cudaMemcpyAsync(tot_host, tot, sizeof(DevTotals), cudaMemcpyDeviceToHost, st));
         BH_TRY(cudaStreamSynchronize(st));
         BH_TRY(cudaGetLastError());
+        if (!counts_on_host) {       // the last build was sync-free: its counts arrive only now
+            n_in = sc_host->n_in; n_internal = sc_host->n_internal; M = n_in + n_internal;
+            ctr.n_in_tree = n_in; ctr.n_out_of_box = n - n_in; ctr.n_internal = n_internal; ctr.n_cells = M;
+            ctr.n_jitter_bodies = sc_host->n_jitter; ctr.max_depth = sc_host->max_depth; ctr.key_levels = root.levels;
+            const bool any = sc_host->bb[0] != 0;
+            ctr.bbox_max_x = any ? bh_ord_unkey(sc_host->bb[0]) : nan(""); ctr.bbox_min_x = any ? bh_ord_unkey(~sc_host->bb[1]) : nan("");
+            ctr.bbox_max_y = any ? bh_ord_unkey(sc_host->bb[2]) : nan(""); ctr.bbox_min_y = any ? bh_ord_unkey(~sc_host->bb[3]) : nan("");
+            jitter_active = sc_host->n_jitter > 0;
+            counts_on_host = true;
+        }
         ctr.interactions = (int64_t)sc_host->interactions;
         ctr.opened = (int64_t)sc_host->opened;
         ctr.exact_retests = (int64_t)sc_host->retests;
@@ -700,13 +760,14 @@ void bh_engine::collect(EvSlot& sl) {
     cudaEventSynchronize(sl.e[9]);
     cudaEvent_t* keep = ev;
     ev = sl.e;
-    const float phases = add_phase_times(0) + add_phase_times(4);
+    const float phases = sl.phases ? add_phase_times(0) + add_phase_times(4) : 0.f;   // (a step replayed from a graph has no phase events)
     float total = 0.f, c = 0.f, mg = 0.f;
     // kick/drift (+ exchange, merge) = whole step minus the build and walk phases
     if (cudaEventElapsedTime(&total, ev[8], ev[9]) == cudaSuccess && total > phases) ctr.ms_integrate += total - phases;
     if (sl.has_comm && cudaEventElapsedTime(&c, ev[12], ev[13]) == cudaSuccess) ctr.ms_comm += c;
     if (sl.has_merge && cudaEventElapsedTime(&mg, ev[14], ev[15]) == cudaSuccess) ctr.ms_merge += mg;
     sl.used = sl.has_comm = sl.has_merge = false;
+    sl.phases = true;
     ev = keep;
 }
 
@@ -719,7 +780,38 @@ int bh_engine::run_steps(int nsteps) {
         cur = &sl; ev = sl.e;
         sl.used = true;
         BH_TRY(cudaEventRecord(ev[8], st));
-        rc = step_once();
+        if (graph_enabled && syncfree_ok(n) && !io_out.armed && !io_wait_in) {
+            // One CUDA graph per step: the launches of the two evaluations and the kicks (45 small kernels and memsets at
+            // the reference's 12,500 bodies, where the step is launch-latency bound) are CAPTURED instead of issued —
+            // the host-side bookkeeping of step_begin / step_end runs as always — and the graph of the previous step is
+            // updated in place with this step's arguments (same topology: a cheap parameter patch; a re-homing step has
+            // another topology and instantiates anew).  The merge rule reads counts back, so it runs behind the graph.
+            BH_RC(prepare_syncfree(n, bh_key_levels(par.root_half)));   // every allocation before the capture
+            capturing = true;
+            cudaError_t ce = cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal);
+            if (ce == cudaSuccess) {
+                rc = step_begin();
+                if (rc == BH_OK) rc = step_end();
+                cudaGraph_t g = nullptr;
+                ce = cudaStreamEndCapture(st, &g);
+                capturing = false;
+                if (rc == BH_OK && ce == cudaSuccess) {
+                    if (gexec) {
+                        cudaGraphExecUpdateResultInfo info;
+                        if (cudaGraphExecUpdate(gexec, g, &info) != cudaSuccess) { cudaGraphExecDestroy(gexec); gexec = nullptr; cudaGetLastError(); }
+                    }
+                    if (!gexec) { ce = cudaGraphInstantiate(&gexec, g, 0); ctr_graph_instantiations++; }
+                    if (ce == cudaSuccess) ce = cudaGraphLaunch(gexec, st);
+                }
+                if (g) cudaGraphDestroy(g);
+            }
+            capturing = false;
+            if (rc == BH_OK && ce != cudaSuccess) rc = cuda_fail(ce, "CUDA graph of a step");
+            sl.phases = false;
+            ctr_graph_steps++;
+            if (rc == BH_OK) rc = step_finish();
+        } else
+            rc = step_once();
         if (rc != BH_OK) { phase = 0; sl.used = false; break; }
         BH_TRY(cudaEventRecord(ev[9], st));
     }
@@ -762,6 +854,8 @@ int bh_create(const bh_config* cfg, bh_engine** out) {
     if (const char* s = getenv("BH_WALK_G")) e->walk_g = atoi(s);
     if (const char* s = getenv("BH_WALK_ACC")) e->walk_acc = atoi(s);
     if (const char* s = getenv("BH_WALK_AFFINE")) e->walk_affine = atoi(s) != 0;
+    if (const char* s = getenv("BH_SYNCFREE")) e->syncfree_enabled = atoi(s) != 0;
+    if (const char* s = getenv("BH_GRAPH")) e->graph_enabled = atoi(s) != 0;
     cudaError_t ce = cudaSetDevice(e->device);
     if (ce == cudaSuccess) ce = cudaStreamCreateWithFlags(&e->st, cudaStreamNonBlocking);
     for (auto& sl : e->ring) for (int k = 0; k < 16 && ce == cudaSuccess; ++k) ce = cudaEventCreate(&sl.e[k]);
@@ -801,6 +895,7 @@ void bh_destroy(bh_engine* e) {
     dev_free(e->snap_xy); dev_free(e->snap_m);
     if (e->snap_hxy) cudaFreeHost(e->snap_hxy);
     if (e->snap_hm) cudaFreeHost(e->snap_hm);
+    if (e->gexec) cudaGraphExecDestroy(e->gexec);
     if (e->comm && bhcomm::api().ok) bhcomm::api().CommDestroy(e->comm);
     e->free_bodies();
     e->free_cells();

@@ -233,6 +233,7 @@ k_count_scan(const uint64_t* __restrict__ keys, int levels, DevScalars* __restri
 // scan values in shared memory for the galloping searches was measured: 81 us against 64 us for the plain
 // L2-resident arrays at 1M bodies, so the searches read the global arrays.)
 __global__ void __launch_bounds__(256) k_emit(BhTreeView t, int levels) {
+    bh_view_resolve(t);
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < t.n_in) bh_emit_body(t, levels, i);
 }
@@ -256,8 +257,10 @@ k_climb_block(BhTreeView t, BhRoot root, const double* __restrict__ x, const dou
     __shared__ BhCellS s_sk[CLIMB_CAP];
     __shared__ double s_m[CLIMB_CAP], s_x[CLIMB_CAP], s_y[CLIMB_CAP];
     __shared__ int s_arr[CLIMB_CAP];
+    bh_view_resolve(t);
     const int tid = threadIdx.x;
     const int b0 = blockIdx.x * CLIMB_B;
+    if (b0 >= t.n_in) return;                    // (sync-free builds launch one block per 256 BODIES, in the tree or not)
     const int b1 = min(b0 + CLIMB_B, t.n_in);
     const int i = b0 + tid;
     const int P0 = t.S[b0] + b0, P1 = t.S[b1] + b1;
@@ -343,6 +346,7 @@ k_climb_block(BhTreeView t, BhRoot root, const double* __restrict__ x, const dou
 // arrive-counter protocol (bh_climb_from).  Runs after k_climb_block, so all local cells are visible.
 __global__ void __launch_bounds__(128)
 k_climb_top(BhTreeView t, BhRoot root, const BhClimbRoot* __restrict__ roots, const int* __restrict__ n_roots) {
+    bh_view_resolve(t);
     const int n = *n_roots;
     for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
         const BhClimbRoot r = roots[k];
@@ -381,6 +385,7 @@ k_walk(BhTreeView t, BhWalkParams w, int first_target, int n_targets, const doub
        const double* __restrict__ y, const double* __restrict__ m, const int* __restrict__ leafpos, double Gc,
        double* __restrict__ ax, double* __restrict__ ay, int* __restrict__ cntI, int* __restrict__ cntO,
        DevScalars* __restrict__ sc, DevTotals* __restrict__ tot, BhWalkQueue q) {
+    bh_view_resolve(t);
     const int lane = threadIdx.x & 31;
     unsigned int smid;
     asm("mov.u32 %0, %%smid;" : "=r"(smid));
@@ -608,6 +613,10 @@ __global__ void k_leaf_depth(BhTreeView t, const int* __restrict__ leafpos, cons
 __global__ void __launch_bounds__(128)
 k_jitter(const uint64_t* __restrict__ keys, int* __restrict__ order, int n_in, BhRoot root, const int* __restrict__ perm,
          double* __restrict__ x, double* __restrict__ y, int* __restrict__ jflag, DevScalars* __restrict__ sc) {
+    if (n_in < 0) {                              // sync-free build: counts on the device; nothing to do without equal keys
+        if (sc->n_jitter == 0) return;
+        n_in = sc->n_in;
+    }
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_in - 1) return;
     const uint64_t k = keys[i];

@@ -1,35 +1,30 @@
-"""configs[0] of BASELINE.json: the reference's own two-disk scene (12,500 bodies, merge rule on,
-reference defaults except theta = 0.5) — steps/s of the CUDA engine and of the CPU oracle."""
+#!/usr/bin/env python
+"""BASELINE.json configs[0]: the reference's own scene (12,500 bodies, merge rule on, theta 0.5) — steps/s of the
+CUDA engine with per-step CUDA graphs (default), with sync-free builds but single launches (BH_GRAPH=0) and with
+the host round trip per build (BH_SYNCFREE=0)."""
 import json
 import os
 import sys
 import time
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-import bh_b200
-from bh_b200 import scenes
+import bh_b200  # noqa: E402
+from bh_b200 import scenes  # noqa: E402
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-
-
-def run(lib, steps, warm):
-    e = bh_b200.NativeEngine(lib=lib)
-    e.set_params(theta=0.5)                      # merge 4000 / 8 px stays on (reference default)
-    e.set_bodies(*scenes.snap_f32(scenes.default_two_disks(seed=1)))
-    e.step(warm)
-    e.reset_counters()
-    t0 = time.perf_counter()
-    e.step(steps)
-    dt = time.perf_counter() - t0
-    c = e.counters()
-    return {"steps_per_s": steps / dt, "ms_per_step": dt / steps * 1e3, "interactions_per_s": c["total_interactions"] / dt,
-            "bodies_left": e.n, "merged": c["total_merged"], "launches_per_step": c["kernel_launches"] / steps,
-            "device_ms_per_step": {k: c[k] / steps for k in ("ms_build", "ms_walk", "ms_integrate", "ms_merge")},
-            "device_ms_per_step_total": c["ms_step_call"] / steps}
-
-
-if __name__ == "__main__":
-    out = {"gpu": run(bh_b200.load_cuda_library(), 500, 20)}
-    if "--cpu" in sys.argv:
-        out["cpu_oracle"] = run(bh_b200.bind(os.path.join(ROOT, "oracle", "libbh_ref.so")), 30, 2)
-    print(json.dumps(out))
+scene = scenes.snap_f32(scenes.default_two_disks(seed=1))
+for label, env in (("graph per step", {}), ("sync-free builds, single launches", {"BH_GRAPH": "0"}), ("host round trip per build", {"BH_SYNCFREE": "0"})):
+    for k in ("BH_GRAPH", "BH_SYNCFREE"):
+        os.environ.pop(k, None)
+    os.environ.update(env)
+    for merge in (8.0, 0.0):
+        e = bh_b200.NativeEngine(device=0)
+        e.set_params(theta=0.5, merge_min_dist=merge)
+        e.set_bodies(*scene)
+        e.step(20)
+        t0 = time.perf_counter()
+        e.step(400)
+        dt = time.perf_counter() - t0
+        c = e.counters()
+        print(json.dumps({"mode": label, "merge_rule": merge > 0, "steps_per_s": 400 / dt, "ms_per_step": dt / 400 * 1e3, "bodies_left": e.n,
+                          "kernel_launches_per_step": c["kernel_launches"] / c["total_steps"]}), flush=True)
+        e.close()
