@@ -51,7 +51,7 @@ inline int bh_engine::let_partition() {
     int64_t max_slice = 0;
     for (int r = 0; r < world; ++r) max_slice = std::max(max_slice, let.cut[r + 1] - let.cut[r]);
     const int64_t room = (cap - max_slice) / (world - 1);
-    let.stray_cap = std::max<int64_t>(n / world / 128, std::min<int64_t>(1024, room));
+    let.stray_cap = std::min<int64_t>(room, std::max<int64_t>(n / world / 64, 1024));
     if (let.stray_cap < 16 || let.stray_cap > room) return BH_OK;
     if (const char* sc_env = getenv("BH_LET_STRAY_CAP")) let.stray_cap = std::max(1, atoi(sc_env));   // test hook: force overflows -> fallbacks
     let.seg_len = LET_SEG_HDR + let.bw + 4 * let.stray_cap;
@@ -273,6 +273,9 @@ inline int bh_engine::let_evaluate(int slot) {
         }
     }
     let.last_strays = let.hcollect[38];
+    // strays accumulate between re-homings (fast galactic cores): re-home at the next evaluation BEFORE the segment
+    // overflows — a scheduled re-homing costs one replicated build, an overflow that plus the wasted evaluation
+    if (let.last_strays * 10 > let.stray_cap * 6) rehome_due = true;
     let.jret_total += let.hcollect[36];
     let.returns_applied = let.hcollect[37] > 0;
     let.n_items = let.hcollect[0];

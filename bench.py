@@ -267,29 +267,47 @@ def parity_check(eng, world, allsum, allmin):
     """N > 1 self-check on the state the timed region left behind: this rank's slice evaluated in DOMAIN mode
     (locally essential tree) and over the REPLICATED tree must give bit-identical accelerations, and the
     interaction counts summed over the ranks must equal what ONE rank counts walking every body over the
-    replicated tree."""
+    replicated tree.  A build may MUTATE positions (the reference's jitter regime, BarnesHutAlg.kt:145-156: a few
+    bodies per build at 8M bodies in this window), so every evaluation starts from the same saved slice state
+    (bh_step_io_slice with 0 steps restores it without touching the partition)."""
+    eng.evaluate_slice()                               # absorbs a pending re-homing: the slices are stable from here on
+    n = eng.n
+    snap = [np.empty(n) for _ in range(5)]
+    k = eng.step_io_slice(0, out=snap)                 # this rank's slice as it is now
+    snap = [a[:k].copy() for a in snap]
+    epoch = eng.slice_epoch()
+
+    def restore():
+        eng.step_io_slice(0, inputs=snap)
+
     eng.reset_counters()
     ax_d, ay_d, ui_d = eng.evaluate_slice()
     cd = eng.counters()
     ls = eng.let_stats()
-    domain_ran = ls["let_evaluations"] > 0 and cd["total_evaluations"] == 1
+    domain_ran = ls["let_evaluations"] > 0 and ls["fallbacks"] == 0
+    restore()
     eng.set_domain_mode(False)
     eng.reset_counters()
     ax_r, ay_r, ui_r = eng.evaluate_slice()
     cr = eng.counters()
+    restore()
     eng.reset_counters()
     fx, fy = eng.compute_accelerations()              # every body, on every rank, over the replicated tree
     cf = eng.counters()
+    restore()
     eng.set_domain_mode(True)
+    stable = allmin(1.0 if eng.slice_epoch() == epoch else 0.0) == 1.0
     same_slice = len(ui_d) == len(ui_r) and bool((ui_d == ui_r).all())
     bit_dr = same_slice and bool(np.array_equal(ax_d, ax_r, equal_nan=True) and np.array_equal(ay_d, ay_r, equal_nan=True))
     bit_full = bool(np.array_equal(ax_d, fx[ui_d], equal_nan=True) and np.array_equal(ay_d, fy[ui_d], equal_nan=True))
     inter_d, inter_r = allsum(float(cd["interactions"])), allsum(float(cr["interactions"]))
-    open_d = allsum(float(cd["opened"]))
+    open_d, open_r = allsum(float(cd["opened"])), allsum(float(cr["opened"]))
     return {"mode": "domain (LET) vs replicated tree, same ranks, same state" if domain_ran else "replicated tree only (domain mode did not run)",
-            "bodies_checked_per_rank": int(len(ui_d)),
-            "interactions_equal": bool(inter_d == inter_r == float(cf["interactions"]) and open_d == float(cf["opened"])),
+            "bodies_checked_per_rank": int(len(ui_d)), "slices_stable_during_the_check": bool(stable),
+            "jitter_bodies_in_the_builds": int(cf["n_jitter_bodies"]),
+            "interactions_equal": bool(inter_d == inter_r == float(cf["interactions"]) and open_d == open_r == float(cf["opened"])),
             "interactions": {"domain_sum_over_ranks": inter_d, "replicated_sum_over_ranks": inter_r, "one_rank_all_bodies": float(cf["interactions"])},
+            "opened": {"domain_sum_over_ranks": open_d, "replicated_sum_over_ranks": open_r, "one_rank_all_bodies": float(cf["opened"])},
             "acc_bit_identical": bool(allmin(1.0 if (bit_dr and bit_full) else 0.0) == 1.0),
             "acc_bit_identical_domain_vs_replicated_slice": bool(allmin(1.0 if bit_dr else 0.0) == 1.0),
             "acc_bit_identical_vs_one_rank_walking_all_bodies": bool(allmin(1.0 if bit_full else 0.0) == 1.0)}
@@ -463,43 +481,33 @@ def main():
                "steps_per_s_separate_calls": e2e_steps / seq_wall}
     else:
         # N > 1: SHARDED I/O — every rank moves only the bodies of its own slice (bh_step_io_slice): the slice's state goes
-        # up from pinned host memory, one step runs, the slice's new state comes down; when a re-homing re-cut the
-        # slices (bh_slice_epoch) the rank fetches the new index and re-gathers its host arrays, inside the timed region
-        torch.set_num_threads(max(1, min(16, (os.cpu_count() or 1) // world)))   # (torchrun pins OMP_NUM_THREADS to 1)
-        full = [torch.from_numpy(a) for a in eng.get_bodies()]            # state after the device-resident steps
-        hs_t = [torch.empty(n, dtype=torch.float64).pin_memory() for _ in range(5)]
-        hslice = [t.numpy() for t in hs_t]
+        # up from pinned host memory, one step runs, the slice's new state comes down
+        # (like PhysicsEngine's own loop — getBodies, step, getBodies — the slice that comes down is the slice that goes
+        # up next: the host owns the state between steps, and bodies that migrated to another rank at a re-homing
+        # simply arrive in that rank's output)
+        hslice = [torch.empty(n, dtype=torch.float64).pin_memory().numpy() for _ in range(5)]
         oslice = [torch.empty(n, dtype=torch.float64).pin_memory().numpy() for _ in range(5)]
-
-        def regather():
-            idx = torch.from_numpy(eng.slice_index().astype(np.int64))
-            for dst, src in zip(hs_t, full):
-                torch.index_select(src, 0, idx, out=dst[:len(idx)])
-            return len(idx), eng.slice_epoch()
-
-        k, epoch = regather()
-        eng.step_io_slice(1, inputs=[a[:k] for a in hslice], out=oslice)
-        k, epoch = regather()
+        k = eng.step_io_slice(0, out=hslice)                  # this rank's slice after the device-resident steps
+        k2 = eng.step_io_slice(1, inputs=[a[:k] for a in hslice], out=oslice)
+        hslice, oslice, k = oslice, hslice, k2
         eng.reset_counters()
         h2d = d2h = 0
-        regathers = 0
+        epoch0 = eng.slice_epoch()
         barrier()
         t0 = time.perf_counter()
         for _ in range(e2e_steps):
-            if eng.slice_epoch() != epoch:
-                k, epoch = regather()
-                regathers += 1
-            k_out = eng.step_io_slice(1, inputs=[a[:k] for a in hslice], out=oslice)
+            k2 = eng.step_io_slice(1, inputs=[a[:k] for a in hslice], out=oslice)
             h2d += 5 * 8 * k
-            d2h += 5 * 8 * k_out
+            d2h += 5 * 8 * k2
+            hslice, oslice, k = oslice, hslice, k2
         barrier()
         e2e_wall = allmax(time.perf_counter() - t0)
         e2e_inter = allsum(float(eng.counters()["total_interactions"]))
         e2e = {"value": e2e_inter / e2e_wall, "unit": "interactions/s", "steps_per_s": e2e_steps / e2e_wall,
                "h2d_bytes_per_step": allsum(float(h2d)) / e2e_steps, "d2h_bytes_per_step": allsum(float(d2h)) / e2e_steps, "steps": e2e_steps,
-               "api": "bh_step_io_slice(1, slice in, slice out) per step on every rank: only the rank's own bodies cross PCIe (pinned host arrays); "
-                      "slice index re-fetched and host arrays re-gathered when a re-homing re-cut the slices",
-               "slice_regathers_in_timed_region": regathers}
+               "api": "bh_step_io_slice(1, slice in, slice out) per step on every rank: only the rank's own bodies cross PCIe (pinned host arrays, "
+                      "transfers overlapped with the compute); the slice that comes down is the slice that goes up at the next step",
+               "re_homings_in_timed_region": eng.slice_epoch() - epoch0}
 
     # ---- N > 1: the run checks itself (domain mode vs replicated tree vs one rank walking every body) -----------
     pcheck = None

@@ -93,10 +93,15 @@ def key_levels(root_half):
     return d
 
 
-# ---- the acceleration-parity metric ------------------------------------------
+# ---- the acceleration-parity metric (distributions: profiles/r02q_acc_error.json) -----------------
 ACC_TOL = 1.0e-5       # north_star: "per-body acceleration within 1e-5 relative (FP32 vs f64)"
-ACC_FLOOR = 0.05       # relative to max(|a_i|, ACC_FLOOR * rms|a|): the relative error of a
-                       # body whose net force cancels to ~0 is unbounded in any FP32 scheme
+ACC_FLOOR_H3 = 1.0e-3  # relative to max(|a_i|, 1e-3 * rms|a|).  Holds where forces do not cancel (disk
+                       # scenes: measured max 3.1e-6 at C1, 6.3e-7 at C3 with 10M bodies)
+ACC_FLOOR = 0.05       # uniform clouds: sum|a_ij| / |a_i| ~ 40 and some bodies have |a_i| << rms, so the per-term FP32
+                       # rounding (an ABSOLUTE error of <= 4.1e-7 * rms|a| on the 1M-body cloud, whichever way it is
+                       # summed) is unbounded RELATIVE to |a_i|: there the gate is floor 0.05 for every body PLUS at
+                       # most ACC_FRAC_ABOVE of the bodies above 1e-5 without any floor (measured 1.0e-4)
+ACC_FRAC_ABOVE = 2.0e-4
 
 
 def acc_errors(ax, ay, gx, gy):
@@ -106,19 +111,30 @@ def acc_errors(ax, ay, gx, gy):
     tiny = 1e-300
     rel = err / np.maximum(a, tiny)
     relf = err / np.maximum(np.maximum(a, ACC_FLOOR * rms), tiny)
+    relh = err / np.maximum(np.maximum(a, ACC_FLOOR_H3 * rms), tiny)
     return {
         "median": float(np.median(rel)) if len(a) else 0.0,
         "p99": float(np.quantile(rel, 0.99)) if len(a) else 0.0,
         "max_unfloored": float(rel.max()) if len(a) else 0.0,
         "max_floored": float(relf.max()) if len(a) else 0.0,
+        "max_floored_h3": float(relh.max()) if len(a) else 0.0,
+        "max_abs_over_rms": float(err.max() / max(rms, tiny)) if len(a) else 0.0,
         "normwise": float(np.sqrt((err ** 2).sum() / max((a ** 2).sum(), tiny))),
         "frac_above_tol_unfloored": float((rel > ACC_TOL).mean()) if len(a) else 0.0,
     }
 
 
-def assert_acc_parity(ax, ay, gx, gy, what=""):
+def assert_acc_parity(ax, ay, gx, gy, what="", cancelling=None):
+    """`cancelling`: the scene is a uniform cloud (net forces cancel); default: decided from the label."""
     s = acc_errors(ax, ay, gx, gy)
-    assert s["max_floored"] <= ACC_TOL, (what, s)
+    if cancelling is None:
+        cancelling = not any(k in what for k in ("disk", "C1", "merger", "mixed"))
     assert s["normwise"] <= 1e-6, (what, s)
     assert s["p99"] <= ACC_TOL, (what, s)
+    assert s["max_floored"] <= ACC_TOL, (what, s)
+    if cancelling:
+        assert s["frac_above_tol_unfloored"] <= max(ACC_FRAC_ABOVE, 3.0 / max(1, len(ax))), (what, s)
+        assert s["max_floored_h3"] <= 1e-3, (what, s)
+    else:
+        assert s["max_floored_h3"] <= ACC_TOL, (what, s)       # SURVEY H3's own gate
     return s

@@ -369,6 +369,15 @@ def test_acceleration_reuse_is_result_identical(cuda_lib):
         e.step(3)
         e.set_bodies(*e.get_bodies())           # resetBodies
         e.step(2)
+        # a build BETWEEN steps that re-homes the state (the 8th step since the last re-homing set rehome_due): the
+        # accelerations on file are in the old home order and must not be reused (round-1 advisor finding)
+        e.set_params(merge_min_dist=0.0)
+        e.step(8 - e.counters()["total_steps"] % 8 if e.counters()["total_steps"] % 8 else 8)
+        e.build_tree()
+        e.step(2)
+        e.direct_sum()                          # invalidates the tree; the overlay then rebuilds it (and may re-home)
+        e.tree()
+        e.step(9)
         engines.append(e)
     a, b = engines[0].get_bodies(), engines[1].get_bodies()
     for u, v in zip(a, b):
