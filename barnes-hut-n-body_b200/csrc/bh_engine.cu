@@ -359,8 +359,12 @@ struct bh_engine {
         let.view_valid = false;
         root = BhRoot{par.root_cx, par.root_cy, par.root_half, bh_key_levels(par.root_half)};
         const int nn = (int)n;
-        if (!let.local_build) { BH_RC(sync_positions()); BH_RC(sync_masses()); }   // a replicated build needs every body's position and mass
-        if (rehome_due && nn > 0) { BH_RC(sync_velocities()); BH_RC(wait_inputs()); }
+        if (!let.local_build) {   // a replicated build needs every body's position and mass
+            BH_RC(sync_positions());
+            if (world > 1 && !mass_valid) BH_RC(wait_inputs());   // bh_step_io_slice: this slice's masses may still be in flight on the copy stream
+            BH_RC(sync_masses());
+        }
+        if (rehome_due && nn > 0) { BH_RC(wait_inputs()); BH_RC(sync_velocities()); }   // (uploaded velocities first, then their exchange)
         if (timed && !capturing) BH_TRY(cudaEventRecord(ev[slot + 0], st));
         bool rehomed = false;
         // zero: scalars | sort scratch (sized for this n) | scan status
@@ -505,7 +509,7 @@ struct bh_engine {
     bool walk_affine = true;        // BH_WALK_AFFINE=0: every chunk from the global queue (no SM affinity)
     unsigned int* walk_queue = nullptr;   // work counters of the persistent walk kernel
     int walk_minb = 7;              // BH_WALK_MINB=8: the pair walk compiled for 8 blocks/SM (64 registers, small spills)
-    int walk_acc = -1;              // BH_WALK_ACC=1: f64 summation (BH_ACC_F64) also for one body per lane
+    int walk_acc = -1;              // BH_WALK_ACC=0: FP32 partial sums (BH_ACC_FOLD) for one body per lane instead of f64 sums
 
     int sort_pairs(int nn, int key_bits) {
         // the sort zeroes nothing itself here: build() already cleared the scratch region
@@ -541,13 +545,15 @@ struct bh_engine {
             // bodies per thread (bh_walk_multi): the widest group that still gives every SM >= 2 full waves of
             // 128-thread blocks; few targets -> one body per lane.  BH_WALK_G pins it (measurements).
             // bodies per thread: pairs (sharing every record load) when there are enough targets to fill the machine
-            // with half the threads, else one body per lane.  Pairs add every term to an f64 sum at once (BH_ACC_F64),
-            // which keeps a body's result independent of its partner; a single body folds FP32 partial sums every
-            // BH_WALK_CHUNK of its own visits (BH_ACC_FOLD).  BH_WALK_G / BH_WALK_ACC pin the choice (tests).
+            // with half the threads, else one body per lane.  Every term is added to an f64 sum at once (BH_ACC_F64) in
+            // BOTH shapes: a body's result then depends neither on its partner nor on which shape its rank's slice
+            // happened to get, so any partition of the targets reproduces one GPU bit for bit.  (One body per lane is
+            // L1-bound: the f64 summation costs it nothing, measured.)  BH_WALK_G pins the shape; BH_WALK_ACC=0 selects
+            // FP32 partial sums folded every BH_WALK_CHUNK visits for one body per lane (tests, measurements).
             int g = walk_g;
             if (g == 0) g = count >= (int64_t)num_sms * 128 * 16 ? 2 : 1;
             g = g >= 2 ? 2 : 1;
-            const bool f64acc = walk_acc == BH_ACC_F64 || (walk_acc < 0 && g > 1) || g > 1;
+            const bool f64acc = g > 1 || walk_acc != BH_ACC_FOLD;
             // persistent SM-affine schedule (see k_walk): one range of chunks per SM, stealing between ranges
             BhWalkQueue q;
             q.next = walk_queue;
@@ -1320,8 +1326,11 @@ int bh_step_io_slice(bh_engine* e, int32_t nsteps, int64_t n_in, const double* x
             e->io_wait_in = true;
         }
         e->tree_valid = false; e->acc_valid = false; e->heavies_valid = false;
-        if (e->world > 1) { e->let.pos_valid = false; e->vel_valid = false; e->mass_valid = false; }
     }
+    // The call is COLLECTIVE (every rank makes it, with or without inputs): each rank treats the other slices as stale,
+    // so that all ranks enter the same exchanges (positions / masses / velocities) at the next replicated build even
+    // if only some of them brought new state.
+    if (e->world > 1) { e->let.pos_valid = false; e->vel_valid = false; e->mass_valid = false; }
     const bool want_out = x_out || y_out || vx_out || vy_out || m_out;
     if (want_out && cap_out < hi - lo) return e->fail(BH_E_ARG, "bh_step_io_slice: capacity too small");
     // the last drift triggers the read-back of the slice's (x, y, m) on the copy stream, under the last evaluation

@@ -5,7 +5,10 @@
 #define LET_GROW(field, need) BH_TRY(let_grow(let.field, let.field##_cap, (int64_t)(need)))
 
 inline bool bh_engine::let_usable() const {
-    return let.enabled && world >= let.min_world && world <= 16 && transport == T_NCCL && !merge_enabled();
+    // from min_world ranks up (4: below, replicating a few-times-larger tree is cheaper than assembling a LET), or from 2
+    // ranks when the replicated build itself is the cost (32 M bodies and more: measured at C4, 100 M bodies on 2 ranks)
+    return let.enabled && (world >= let.min_world || (world >= 2 && n >= ((int64_t)32 << 20))) && world <= 16 && transport == T_NCCL &&
+           !merge_enabled();
 }
 inline bool bh_engine::let_ready() const {
     return let_usable() && let.part_valid && let.n_part == n && !rehome_due && let.part_root.cx == par.root_cx &&
@@ -273,9 +276,8 @@ inline int bh_engine::let_evaluate(int slot) {
         }
     }
     let.last_strays = let.hcollect[38];
-    // strays accumulate between re-homings (fast galactic cores): re-home at the next evaluation BEFORE the segment
-    // overflows — a scheduled re-homing costs one replicated build, an overflow that plus the wasted evaluation
-    if (let.last_strays * 10 > let.stray_cap * 6) rehome_due = true;
+    // (NOT a place to schedule an early re-homing from: this is THIS rank's count, and every rank must take the same
+    // branch into the collectives of the next build — an overflow is agreed on through the all-reduced retry flags)
     let.jret_total += let.hcollect[36];
     let.returns_applied = let.hcollect[37] > 0;
     let.n_items = let.hcollect[0];

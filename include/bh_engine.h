@@ -323,8 +323,9 @@ int bh_import_slices(bh_engine* e, int32_t field, int64_t n, const double* a, co
  *   bh_step_io_slice: [slice state in: x, y, vx, vy, m of the slice, home order; NULL = keep] ; nsteps x step() ;
  *   [slice state out].  The rest of the state is exchanged between the ranks by the engine as the mode needs it
  *   (nothing in domain mode; positions / masses / velocities of the other slices before a replicated build).
- * With one rank the slice is the whole list (in home order).  Refused while the merge rule is enabled on more than
- * one rank (removals re-index the list on every rank). */
+ * With one rank the slice is the whole list (in home order).  The call is COLLECTIVE: every rank makes it (with or
+ * without inputs).  Refused while the merge rule is enabled on more than one rank (removals re-index the list on
+ * every rank). */
 int bh_get_slice_index(bh_engine* e, int64_t cap, int32_t* user_index, int64_t* n_slice);
 int64_t bh_slice_epoch(const bh_engine* e);
 int bh_step_io_slice(bh_engine* e, int32_t nsteps, int64_t n_in,

@@ -369,15 +369,6 @@ def test_acceleration_reuse_is_result_identical(cuda_lib):
         e.step(3)
         e.set_bodies(*e.get_bodies())           # resetBodies
         e.step(2)
-        # a build BETWEEN steps that re-homes the state (the 8th step since the last re-homing set rehome_due): the
-        # accelerations on file are in the old home order and must not be reused (round-1 advisor finding)
-        e.set_params(merge_min_dist=0.0)
-        e.step(8 - e.counters()["total_steps"] % 8 if e.counters()["total_steps"] % 8 else 8)
-        e.build_tree()
-        e.step(2)
-        e.direct_sum()                          # invalidates the tree; the overlay then rebuilds it (and may re-home)
-        e.tree()
-        e.step(9)
         engines.append(e)
     a, b = engines[0].get_bodies(), engines[1].get_bodies()
     for u, v in zip(a, b):
@@ -667,3 +658,28 @@ def test_sharded_slice_io_equals_full_state_io(cuda_lib):
     assert len(epochs) >= 2                         # re-homings happened in between
     with pytest.raises(bh_b200.BhError):
         e.step_io_slice(1, inputs=[a[:10] for a in state], out=out)     # not the slice length
+
+
+def test_acceleration_reuse_survives_builds_between_steps(cuda_lib):
+    """BH_FLAG_REUSE_ACC and a build BETWEEN steps (round-1 advisor finding): when the 8th step since the last re-homing
+    has set `rehome_due`, a `bh_build_tree` — or the overlay's rebuild after `bh_direct_sum` dropped the tree — re-homes
+    the state; the accelerations on file are then in the OLD home order and must not be reused by the next step."""
+    import bh_b200
+    scene = scenes.snap_f32(scenes.default_two_disks(n1=2500, n2=700, seed=52))
+    engines = []
+    for flags in (0, bh_b200.BH_FLAG_REUSE_ACC):
+        e = bh_b200.NativeEngine(lib=cuda_lib, flags=flags)
+        e.set_params(theta=0.5, merge_min_dist=0.0)
+        e.set_bodies(*scene)
+        e.step(8)                               # the 8th step since the first build's re-homing: a re-homing is due
+        e.build_tree()                          # ... and happens HERE, between two steps
+        e.step(7)
+        e.step(1)                               # due again
+        e.direct_sum()                          # invalidates the tree; the overlay then rebuilds it (and re-homes)
+        e.tree()
+        e.step(9)
+        engines.append(e)
+    a, b = engines[0].get_bodies(), engines[1].get_bodies()
+    for u, v in zip(a, b):
+        assert (u == v).all()
+    assert engines[1].counters()["total_evaluations"] < engines[0].counters()["total_evaluations"]
