@@ -509,7 +509,7 @@ struct bh_engine {
     bool walk_affine = true;        // BH_WALK_AFFINE=0: every chunk from the global queue (no SM affinity)
     unsigned int* walk_queue = nullptr;   // work counters of the persistent walk kernel
     int walk_minb = 7;              // BH_WALK_MINB=8: the pair walk compiled for 8 blocks/SM (64 registers, small spills)
-    int walk_acc = -1;              // BH_WALK_ACC=0: FP32 partial sums (BH_ACC_FOLD) for one body per lane instead of f64 sums
+    int walk_acc = -1;              // BH_WALK_ACC=1: f64 summation (BH_ACC_F64) also for one body per lane
 
     int sort_pairs(int nn, int key_bits) {
         // the sort zeroes nothing itself here: build() already cleared the scratch region
@@ -542,18 +542,17 @@ struct bh_engine {
         if (!capturing) BH_TRY(cudaEventRecord(ev[slot + 2], st));
         if (count > 0) {
             const BhWalkParams w = bh_walk_params(par.theta, par.soft2, par.root_half);
-            // bodies per thread (bh_walk_multi): the widest group that still gives every SM >= 2 full waves of
-            // 128-thread blocks; few targets -> one body per lane.  BH_WALK_G pins it (measurements).
-            // bodies per thread: pairs (sharing every record load) when there are enough targets to fill the machine
-            // with half the threads, else one body per lane.  Every term is added to an f64 sum at once (BH_ACC_F64) in
-            // BOTH shapes: a body's result then depends neither on its partner nor on which shape its rank's slice
-            // happened to get, so any partition of the targets reproduces one GPU bit for bit.  (One body per lane is
-            // L1-bound: the f64 summation costs it nothing, measured.)  BH_WALK_G pins the shape; BH_WALK_ACC=0 selects
-            // FP32 partial sums folded every BH_WALK_CHUNK visits for one body per lane (tests, measurements).
+            // Bodies per thread (bh_walk_multi): pairs sharing every record load, each term added to an f64 sum at once
+            // (BH_ACC_F64: a body's result does not depend on its partner), when the LIST is long enough to fill the
+            // machine with half the threads; else one body per lane folding FP32 partial sums every BH_WALK_CHUNK of
+            // its own visits (BH_ACC_FOLD).  The choice is made from the length of the whole list, n — the same number
+            // on every rank and for every world size — never from this call's `count`: all ranks and all partitions
+            // of the targets then run the same arithmetic and reproduce one GPU bit for bit.  BH_WALK_G pins the shape,
+            // BH_WALK_ACC=1 selects the f64 summation for one body per lane as well (tests, measurements).
             int g = walk_g;
-            if (g == 0) g = count >= (int64_t)num_sms * 128 * 16 ? 2 : 1;
+            if (g == 0) g = n >= (int64_t)num_sms * 128 * 16 ? 2 : 1;
             g = g >= 2 ? 2 : 1;
-            const bool f64acc = g > 1 || walk_acc != BH_ACC_FOLD;
+            const bool f64acc = g > 1 || walk_acc == BH_ACC_F64;
             // persistent SM-affine schedule (see k_walk): one range of chunks per SM, stealing between ranges
             BhWalkQueue q;
             q.next = walk_queue;
@@ -992,6 +991,7 @@ int bh_get_bodies(bh_engine* e, int64_t cap, double* x, double* y, double* vx, d
     if (e->n > 0) {
         E_RC(e->sync_positions());
         if (vx || vy) E_RC(e->sync_velocities());
+        E_RC(e->sync_masses());             // (stale only after bh_step_io_slice brought new masses for the slices)
         // one staging buffer: each scatter is stream-ordered behind the previous copy
         E_RC(e->download_user(x, e->x, e->dtmp)); E_RC(e->download_user(y, e->y, e->dtmp));
         E_RC(e->download_user(vx, e->vx, e->dtmp)); E_RC(e->download_user(vy, e->vy, e->dtmp));
@@ -1027,6 +1027,7 @@ int bh_get_positions_f32(bh_engine* e, int64_t cap, float* xy, float* m, int64_t
     if (e->n == 0) return BH_OK;
     E_TRY(cudaSetDevice(e->device));
     E_RC(e->sync_positions());
+    E_RC(e->sync_masses());
     // staged in user order through dtmp (float2[n]) and itmp (float[n])
     float2* dxy = reinterpret_cast<float2*>(e->dtmp);
     float* dm = reinterpret_cast<float*>(e->itmp);
@@ -1057,6 +1058,7 @@ int bh_append_disk(bh_engine* e, int64_t n_total, const bh_disk_params* p, uint6
     const int64_t add = std::max<int64_t>(n_total, 1);   // sats = (nTotal - 1).coerceAtLeast(0), plus the centre
     if (e->n + add >= (int64_t)1 << 30) return e->fail(BH_E_ARG, "more than 2^30 bodies are not supported");
     E_RC(e->sync_positions());
+    E_RC(e->sync_masses());
     E_RC(e->sync_velocities());
     E_RC(e->grow_keep(add));
     const int64_t b = e->n;
@@ -1080,6 +1082,7 @@ int bh_append_uniform_random(bh_engine* e, int64_t n, double m, int32_t w, int32
     E_TRY(cudaSetDevice(e->device));
     if (e->n + n >= (int64_t)1 << 30) return e->fail(BH_E_ARG, "more than 2^30 bodies are not supported");
     E_RC(e->sync_positions());
+    E_RC(e->sync_masses());
     E_RC(e->sync_velocities());
     E_RC(e->grow_keep(n));
     const int64_t b = e->n;
@@ -1112,6 +1115,7 @@ int bh_request_positions_f32(bh_engine* e) {
     if (e->snap_n >= 0) E_TRY(cudaStreamWaitEvent(e->st, e->snap_ev[1], 0));   // previous copy still reads the staging
     e->snap_n = e->n;
     E_RC(e->sync_positions());
+    E_RC(e->sync_masses());
     if (e->n > 0) {
         k_positions_f32<<<grid_for(e->n, 256), 256, 0, e->st>>>(e->x, e->y, e->m, e->perm, (int)e->n, e->snap_xy, e->snap_m);
         e->ctr.kernel_launches += 1;
@@ -1390,6 +1394,7 @@ int bh_direct_sum(bh_engine* e, double* ax, double* ay) {
     E_TRY(cudaSetDevice(e->device));
     if (e->n == 0) return BH_OK;
     E_RC(e->sync_positions());
+    E_RC(e->sync_masses());
     // results go to the sort buffers (not e->ax/ay, which belong to the integrator)
     double* dax = reinterpret_cast<double*>(e->keys_a);
     double* day = reinterpret_cast<double*>(e->keys_b);
@@ -1415,6 +1420,7 @@ int bh_energy(bh_engine* e, double* ke, double* pe, double* px, double* py) {
     if (e->n > 0) {
         E_RC(e->sync_positions());
         E_RC(e->sync_velocities());
+        E_RC(e->sync_masses());
         E_TRY(cudaMemsetAsync(e->red, 0, 4 * sizeof(double), e->st));
         k_energy<<<grid_for(e->n, DS_TILE), DS_TILE, 0, e->st>>>(e->x, e->y, e->vx, e->vy, e->m, (int)e->n, e->par.soft2, e->red);
         e->ctr.kernel_launches += 1;

@@ -40,17 +40,21 @@ def workload(n_gpus, bodies_per_gpu):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    """nvidia-smi clocks / throttle reasons around the timed region (B200_PROFILING.md).  The query loop is started
+    before the warm-up (nvidia-smi needs a few hundred ms to come up, longer with 8 ranks starting one each) and
+    its rows are time-stamped; the report uses the rows that fall inside the timed region widened by one sampling
+    period on either side (a 20-step region is shorter than the 100 ms period), else all rows, and says which."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    PERIOD = 0.1
 
     def __init__(self, gpu_index):
-        self.rows, self.proc, self.gpu = [], None, gpu_index
+        self.rows, self.proc, self.gpu, self.t_begin = [], None, gpu_index, None
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", str(int(self.PERIOD * 1000))],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -59,23 +63,38 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
+
+    def wait_ready(self, timeout=5.0):
+        t_end = time.perf_counter() + timeout
+        while self.proc and not self.rows and time.perf_counter() < t_end and self.proc.poll() is None:
+            time.sleep(0.01)
+
+    def begin(self):
+        self.t_begin = time.perf_counter()
 
     def stop(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        t_stop = time.perf_counter()
+        time.sleep(self.PERIOD + 0.05)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
-        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
-        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        rows = list(self.rows)
+        t0 = self.t_begin if self.t_begin is not None else -1.0
+        near = [r for t, r in rows if t0 - self.PERIOD <= t <= t_stop + self.PERIOD]
+        window = "timed region +- one 100 ms sampling period"
+        if not near:
+            near, window = [r for _, r in rows], "whole run (no sample fell near the timed region)"
+        sm = [float(r[1]) for r in near if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in near if len(r) >= 9 and r[2].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({names[k] for r in self.rows if len(r) >= 9 for k in range(4) if r[5 + k].lower().startswith("active")})
+        reasons = sorted({names[k] for r in near if len(r) >= 9 for k in range(4) if r[5 + k].lower().startswith("active")})
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+                "reasons": reasons, "samples": len(sm), "window": window}
 
 
 def measured_peaks():
@@ -97,6 +116,41 @@ def emit(line):
         sys.stdout.write(data.decode()); sys.stdout.flush()
     else:
         os.write(_REAL_STDOUT, data)
+
+
+class Watchdog:
+    """The headline is measured first; everything after it (end-to-end loop, self-check, the larger configs, the side
+    measurements) runs under a per-phase deadline.  A phase that does not finish (a multi-rank run waiting in a
+    collective, say) must not take the measured headline with it: rank 0 prints the line as far as it got, naming the
+    phase under "incomplete", and every rank leaves with os._exit(0) — each rank runs its own timer from the same
+    barrier-aligned phase starts."""
+
+    def __init__(self, rank):
+        self.rank, self.line, self.deadline, self.name, self.limit = rank, None, None, None, None
+        self.lock = threading.Lock()
+        threading.Thread(target=self._run, daemon=True).start()
+
+    def phase(self, name, seconds):
+        with self.lock:
+            self.name, self.limit, self.deadline = name, seconds, time.monotonic() + seconds
+
+    def done(self):
+        with self.lock:
+            self.deadline = None
+
+    def _run(self):
+        while True:
+            time.sleep(0.5)
+            with self.lock:
+                fired = self.deadline is not None and time.monotonic() > self.deadline
+                if fired and self.rank == 0 and self.line is not None:
+                    self.line["incomplete"] = (f"phase '{self.name}' did not finish within {self.limit} s: the run was cut there, "
+                                               f"the fields it and the later phases fill are null / missing")
+                    emit(self.line)
+                if fired:
+                    sys.stderr.write(f"[bench rank {self.rank}] watchdog: phase '{self.name}' exceeded {self.limit} s\n")
+                    sys.stderr.flush()
+                    os._exit(0)
 
 
 REFERENCE_BUDGET_S = 150.0     # CPU time the whole reference arm may take (warm-up + timed steps)
@@ -402,11 +456,13 @@ def main():
     eng.set_bodies(*scene)
 
     # ---- device-resident throughput: K steps, inputs already in HBM ------------------------
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     eng.step(args.warmup)
     eng.reset_counters()
-    sampler = ClockSampler(local_rank)
+    sampler.wait_ready()
     barrier()
-    sampler.start()
+    sampler.begin()
     t0 = time.perf_counter()
     eng.step(args.steps)
     barrier()
@@ -459,7 +515,34 @@ def main():
                       "traffic": None, "peak_source": peak_src, "ms_per_build": build_ms,
                       "algorithmic_bytes_per_body": bytes_per_body}
 
+    line = {
+        "metric": "body_interactions_per_s", "value": value, "unit": "interactions/s",
+        "steps_per_s": args.steps / (dev_ms * 1e-3), "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dev_ms / args.steps, "wall_ms_per_step": wall / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32 interactions, f64 state/COM/integrator", "data": "synthetic",
+        "config": {"workload": f"{n}-body uniform 'C' cloud ({args.bodies}/GPU), theta={THETA}, {W}x{H} window, G=80, dt=0.005, merge off",
+                   "step": "PhysicsEngine.step(): 2 builds + 2 evaluations + KDK",
+                   "parallelism": "single GPU" if n_gpus == 1 else (
+                       f"domain mode: {n_gpus} Morton ranges, local tree per rank + locally essential tree (all-reduced level summaries, "
+                       f"boundary subtrees {'read over NVLink peer memory (CUDA IPC)' if let_stats.get('enabled') == 2 else 'over NCCL send/recv'}), "
+                       f"re-homing every 8 steps" if let_stats and let_stats["let_evaluations"] > 0 else
+                       f"replicated tree, {n_gpus} Morton slices of targets, NCCL all-gather of positions"),
+                   "l2": "no flush: per-step working set (~210 B/body state+sort+tree) exceeds the 126 MB L2 and is rewritten every build"},
+        "interactions_per_step": inter / args.steps, "opened_per_step": opened / args.steps,
+        "phases_ms_per_evaluation": {"build": build_ms, "walk": walk_ms},
+        "ms_per_step_other": {"exchange": c["ms_comm"] / args.steps, "integrate_and_rest": c["ms_integrate"] / args.steps},
+        "roofline": roofline, "roofline_build": roofline_build, "cpu_baseline": None, "e2e": None, "configs0": None, "reuse_acc_mode": None,
+        "parity_check": None, "configs": [], "roofline_direct": None,
+        "gpu_launches": launches, "clocks": clocks,
+    }
+    if let_stats:
+        line["domain_mode_rank0"] = let_stats
+    wd = Watchdog(rank)
+    wd.line = line
+
     # ---- end to end through the C ABI with HOST buffers --------------------------------------
+    wd.phase("end to end (host buffers through the C ABI)", 120)
     e2e_steps = max(3, min(args.steps, 10))
     if world == 1:
         host = [torch.from_numpy(np.ascontiguousarray(a)).pin_memory() for a in scene]
@@ -521,21 +604,31 @@ def main():
                       "transfers overlapped with the compute); the slice that comes down is the slice that goes up at the next step",
                "re_homings_in_timed_region": eng.slice_epoch() - epoch0}
 
+    line["e2e"] = e2e
+
     # ---- N > 1: the run checks itself (domain mode vs replicated tree vs one rank walking every body) -----------
     pcheck = None
     if world > 1:
+        wd.phase("parity_check (domain mode vs replicated tree vs one rank walking every body)", 180)
+        barrier()
         pcheck = parity_check(eng, world, allsum, allmin)
+        line["parity_check"] = pcheck
+        if pcheck.get("checked") and not (pcheck["interactions_equal"] and pcheck["acc_bit_identical"]):
+            line["parity_failed"] = True                         # a multi-GPU run that disagrees with itself: flagged at the top level
     eng.close()
 
     # ---- BASELINE.json configs[2..4] at this GPU count (strong scaling: the total is fixed) --------------------
-    cfg_records = []
+    cfg_records = line["configs"]
     for name in [c for c in args.configs.split(",") if c]:
         steps_c, warm_c = {"C3": (20, 3), "C4": (8, 2), "C5": (60, 2)}[name]
+        wd.phase(f"config {name}", {"C3": 150, "C4": 300, "C5": 300}[name])
+        barrier()
         try:
             cfg_records.append(run_config(name, steps_c, warm_c, local_rank, rank, world, dist, allmax, allsum, barrier))
         except Exception as ex:                                   # a config must never take the headline down with it
             cfg_records.append({"config": name, "n_gpus": world, "error": f"{type(ex).__name__}: {ex}"[:300]})
             torch.cuda.synchronize()
+    wd.phase("side measurements (reuse mode, configs[0], direct sum, CPU baseline)", 300)
 
     # ---- opt-in BH_FLAG_REUSE_ACC (result-identical, one evaluation per step): reported, not the headline
     reuse = None
@@ -552,6 +645,7 @@ def main():
                  "evaluations_per_step": cr["total_evaluations"] / args.steps,
                  "note": "step n+1 reuses a(t+dt) of step n (bit-identical state); not the reference's cost model, so not the headline"}
         er.close()
+    line["reuse_acc_mode"] = reuse
 
     # ---- BASELINE.json configs[0]: the reference's own scene (12,500 bodies, merge on) ---------
     c1 = None
@@ -565,6 +659,7 @@ def main():
         c1 = {"workload": "reference two-disk scene, 12,500 bodies, theta=0.5, merge rule on", "steps_per_s": 300 / (time.perf_counter() - t0),
               "bodies_left": e1.n}
         e1.close()
+    line["configs0"] = c1
 
     # ---- the device accuracy oracle (tiled all-pairs direct sum, BH.kt:250-259 over every pair): FP32-pipe roofline
     direct = None
@@ -585,6 +680,7 @@ def main():
                            "achieved": tf, "peak": float(fp32[0]), "unit": "TFLOP/s", "frac": tf / float(fp32[0]) if fp32[0] > 0 else None,
                            "algorithmic": "14 flop x N(N-1) pair interactions (SURVEY.md 8(d)); same measured FFMA peak as the walk"})
             ed.close()
+    line["roofline_direct"] = direct
 
     # ---- CPU baseline beside it (rank 0, N = 1 only) ------------------------------------------
     cpu = None
@@ -603,35 +699,15 @@ def main():
                "kind": "port", "steps_per_s": 2 / dt,
                "sample": "2 full steps of the same 1M-body workload (C++ port of BarnesHutAlg.kt; the JVM reference cannot run in this image)"}
         o.close()
+    line["cpu_baseline"] = cpu
 
+    wd.done()
     if rank == 0:
-        line = {
-            "metric": "body_interactions_per_s", "value": value, "unit": "interactions/s",
-            "steps_per_s": args.steps / (dev_ms * 1e-3), "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": dev_ms / args.steps, "wall_ms_per_step": wall / args.steps * 1e3,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32 interactions, f64 state/COM/integrator", "data": "synthetic",
-            "config": {"workload": f"{n}-body uniform 'C' cloud ({args.bodies}/GPU), theta={THETA}, {W}x{H} window, G=80, dt=0.005, merge off",
-                       "step": "PhysicsEngine.step(): 2 builds + 2 evaluations + KDK",
-                       "parallelism": "single GPU" if n_gpus == 1 else (
-                           f"domain mode: {n_gpus} Morton ranges, local tree per rank + locally essential tree (all-reduced level summaries, "
-                           f"boundary subtrees over NCCL send/recv), re-homing every 8 steps" if let_stats and let_stats["let_evaluations"] > 0 else
-                           f"replicated tree, {n_gpus} Morton slices of targets, NCCL all-gather of positions"),
-                       "l2": "no flush: per-step working set (~210 B/body state+sort+tree) exceeds the 126 MB L2 and is rewritten every build"},
-            "interactions_per_step": inter / args.steps, "opened_per_step": opened / args.steps,
-            "phases_ms_per_evaluation": {"build": build_ms, "walk": walk_ms},
-            "ms_per_step_other": {"exchange": c["ms_comm"] / args.steps, "integrate_and_rest": c["ms_integrate"] / args.steps},
-            "roofline": roofline, "roofline_build": roofline_build, "cpu_baseline": cpu, "e2e": e2e, "configs0": c1, "reuse_acc_mode": reuse,
-            "parity_check": pcheck, "configs": cfg_records, "roofline_direct": direct,
-            "gpu_launches": launches, "clocks": clocks,
-        }
-        if let_stats:
-            line["domain_mode_rank0"] = let_stats
         emit(line)
     if world > 1:
         dist.destroy_process_group()
-    if pcheck is not None and pcheck.get("checked") and not (pcheck["interactions_equal"] and pcheck["acc_bit_identical"]):
-        sys.exit(3)                                               # a multi-GPU run that disagrees with itself is not a result
+    if line.get("parity_failed"):
+        sys.stderr.write("[bench] parity_check FAILED: see \"parity_check\" in the JSON line\n")
 
 
 if __name__ == "__main__":

@@ -50,3 +50,26 @@ def test_slice_io_zero_steps_round_trips_the_state(oracle_lib):
     for a, b in zip(e.get_bodies(), ref):
         assert np.array_equal(a, b)
     e.close()
+
+
+def test_watchdog_prints_the_line_and_leaves_when_a_phase_hangs(tmp_path):
+    """A phase after the headline that never returns (ranks waiting in a collective) must not lose the headline."""
+    import json
+    import subprocess
+    import sys
+    code = (
+        "import importlib.util, time\n"
+        f"spec = importlib.util.spec_from_file_location('b', r'{os.path.join(ROOT, 'bench.py')}')\n"
+        "b = importlib.util.module_from_spec(spec); spec.loader.exec_module(b)\n"
+        "wd = b.Watchdog(0); wd.line = {'metric': 'body_interactions_per_s', 'value': 1.0, 'e2e': None}\n"
+        "wd.phase('quick', 30); wd.done()\n"
+        "time.sleep(1.2)\n"                        # a finished phase never fires
+        "wd.phase('stuck', 1)\n"
+        "time.sleep(30)\n"
+        "print('not reached')\n")
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=60)
+    assert r.returncode == 0, r.stderr
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, r.stdout
+    d = json.loads(lines[0])
+    assert d["value"] == 1.0 and "stuck" in d["incomplete"]
