@@ -706,8 +706,9 @@ def main():
         emit(line)
     if world > 1:
         dist.destroy_process_group()
-    if line.get("parity_failed"):
+    if line.get("parity_failed"):                                 # the line is out (flagged "parity_failed"); the exit status says so too
         sys.stderr.write("[bench] parity_check FAILED: see \"parity_check\" in the JSON line\n")
+        sys.exit(3)
 
 
 if __name__ == "__main__":
