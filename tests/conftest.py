@@ -102,6 +102,8 @@ ACC_FLOOR = 0.05       # uniform clouds: sum|a_ij| / |a_i| ~ 40 and some bodies 
                        # summed) is unbounded RELATIVE to |a_i|: there the gate is floor 0.05 for every body PLUS at
                        # most ACC_FRAC_ABOVE of the bodies above 1e-5 without any floor (measured 1.0e-4)
 ACC_FRAC_ABOVE = 2.0e-4
+H3_MEASURED = ("C1 two-disk 12.5k θ0.5", "10M two-disk")    # profiles/r02q_acc_error.json: max 3.1e-6 and 6.3e-7 with floor 1e-3
+CLOUD_MEASURED = ("1M cloud",)                               # ibid.: 1.0e-4 of the bodies above 1e-5 unfloored, max 1.9e-4 with floor 1e-3
 
 
 def acc_errors(ax, ay, gx, gy):
@@ -125,16 +127,18 @@ def acc_errors(ax, ay, gx, gy):
 
 
 def assert_acc_parity(ax, ay, gx, gy, what="", cancelling=None):
-    """`cancelling`: the scene is a uniform cloud (net forces cancel); default: decided from the label."""
+    """Every comparison: norm-wise <= 1e-6, p99 <= 1e-5, max <= 1e-5 relative to max(|a_i|, 0.05 rms).  On top of
+    that, on the BASELINE scenes whose error distribution is on file (profiles/r02q_acc_error.json): SURVEY H3's own
+    gate (max <= 1e-5 relative to max(|a_i|, 1e-3 rms)) on the disk scenes, and on the 1M-body uniform cloud — where
+    net forces cancel and no floor-1e-3 bound of 1e-5 exists for FP32 terms — at most ACC_FRAC_ABOVE of the bodies
+    above 1e-5 WITHOUT any floor and max <= 1e-3 with H3's floor."""
     s = acc_errors(ax, ay, gx, gy)
-    if cancelling is None:      # SURVEY H3's gate where it was measured to hold with a margin (C1, the 10M-body merger)
-        cancelling = not any(k in what for k in ("C1", "10M two-disk"))
     assert s["normwise"] <= 1e-6, (what, s)
     assert s["p99"] <= ACC_TOL, (what, s)
     assert s["max_floored"] <= ACC_TOL, (what, s)
-    if cancelling:
+    if what in H3_MEASURED and not cancelling:
+        assert s["max_floored_h3"] <= ACC_TOL, (what, s)       # SURVEY H3's own gate
+    if what in CLOUD_MEASURED or cancelling:
         assert s["frac_above_tol_unfloored"] <= max(ACC_FRAC_ABOVE, 8.0 / max(1, len(ax))), (what, s)
         assert s["max_floored_h3"] <= 1e-3, (what, s)
-    else:
-        assert s["max_floored_h3"] <= ACC_TOL, (what, s)       # SURVEY H3's own gate
     return s
