@@ -14,6 +14,9 @@
 // uses only IEEE binary64 + - * / sqrt and comparisons, which a strict-FP JVM
 // (JDK >= 17) and g++ -O2 -ffp-contract=off evaluate identically.
 //
+// A second, independent reading of the same source (oracle/bh_ref_second.py: Python objects and
+// recursion) must agree with this one bit for bit: tests/test_oracle_second_reading.py.
+//
 // Every function cites the BarnesHutAlg.kt lines it follows ("BH.kt:a-b").
 #include "../include/bh_engine.h"
 
