@@ -508,7 +508,6 @@ struct bh_engine {
     int walk_g = 0;                 // bodies per thread of the walk; 0 = automatic (BH_WALK_G=1|2 pins it)
     bool walk_affine = true;        // BH_WALK_AFFINE=0: every chunk from the global queue (no SM affinity)
     unsigned int* walk_queue = nullptr;   // work counters of the persistent walk kernel
-    int walk_minb = 7;              // BH_WALK_MINB=8: the pair walk compiled for 8 blocks/SM (64 registers, small spills)
     int walk_acc = -1;              // BH_WALK_ACC=1: f64 summation (BH_ACC_F64) also for one body per lane
 
     int sort_pairs(int nn, int key_bits) {
@@ -564,8 +563,7 @@ struct bh_engine {
 #define BH_LAUNCH_WALK(GG, AA, MINB)                                                                                        \
     k_walk<GG, AA, MINB><<<(int)std::min<int64_t>((q.chunks + 3) / 4, (int64_t)num_sms * MINB), 128, 0, st>>>(              \
         tv, w, (int)first, (int)count, x, y, m, leafpos, par.G, ax, ay, cntI, cntO, sc(), tot, q)
-            if (g == 2 && walk_minb == 8) BH_LAUNCH_WALK(2, BH_ACC_F64, 8);
-            else if (g == 2) BH_LAUNCH_WALK(2, BH_ACC_F64, 7);
+            if (g == 2) BH_LAUNCH_WALK(2, BH_ACC_F64, 7);
             else if (f64acc) BH_LAUNCH_WALK(1, BH_ACC_F64, 9);
             else BH_LAUNCH_WALK(1, BH_ACC_FOLD, 9);
 #undef BH_LAUNCH_WALK
@@ -860,7 +858,6 @@ int bh_create(const bh_config* cfg, bh_engine** out) {
     if (const char* s = getenv("BH_REHOME_INTERVAL")) { const int v = atoi(s); if (v > 0) e->rehome_interval = v; }
     if (const char* s = getenv("BH_WALK_G")) e->walk_g = atoi(s);
     if (const char* s = getenv("BH_WALK_ACC")) e->walk_acc = atoi(s);
-    if (const char* s = getenv("BH_WALK_MINB")) e->walk_minb = atoi(s);
     if (const char* s = getenv("BH_WALK_AFFINE")) e->walk_affine = atoi(s) != 0;
     if (const char* s = getenv("BH_SYNCFREE")) e->syncfree_enabled = atoi(s) != 0;
     if (const char* s = getenv("BH_GRAPH")) e->graph_enabled = atoi(s) != 0;

@@ -18,8 +18,8 @@ s = (n / 1_000_000) ** 0.5
 W, H = int(round(2400 * s)), int(round(800 * s))
 scene = scenes.make_uniform_random(n, 0.5, W, H, seed=3)
 base = None
-for g, acc, aff, minb in [(1, 0, 1, 7), (1, 0, 0, 7), (1, 1, 1, 7), (2, 1, 1, 7), (2, 1, 0, 7), (2, 1, 1, 8)]:
-    os.environ["BH_WALK_G"], os.environ["BH_WALK_ACC"], os.environ["BH_WALK_AFFINE"], os.environ["BH_WALK_MINB"] = str(g), str(acc), str(aff), str(minb)
+for g, acc, aff in [(1, 0, 1), (1, 0, 0), (1, 1, 1), (2, 1, 1), (2, 1, 0)]:
+    os.environ["BH_WALK_G"], os.environ["BH_WALK_ACC"], os.environ["BH_WALK_AFFINE"] = str(g), str(acc), str(aff)
     e = bh_b200.NativeEngine(device=0, capacity_hint=n)
     e.set_window(W, H)
     e.set_params(theta=0.5, merge_min_dist=0.0)
@@ -34,7 +34,7 @@ for g, acc, aff, minb in [(1, 0, 1, 7), (1, 0, 0, 7), (1, 1, 1, 7), (2, 1, 1, 7)
         base = (ax, ay)
     a = np.hypot(*base)
     rel = np.hypot(ax - base[0], ay - base[1]) / np.maximum(a, 1e-3 * np.sqrt(np.mean(a * a)))
-    print(json.dumps({"G": g, "acc": "f64" if acc else "fold", "affine": aff, "blocks_per_sm": minb, "bodies": n, "walk_ms": c["ms_walk"] / 8, "build_ms": c["ms_build"] / 8,
+    print(json.dumps({"G": g, "acc": "f64" if acc else "fold", "affine": aff, "bodies": n, "walk_ms": c["ms_walk"] / 8, "build_ms": c["ms_build"] / 8,
                       "interactions": c["interactions"], "opened": c["opened"],
                       "max_rel_vs_G1_fold": float(rel.max()), "bit_identical_to_G1_fold": bool((ax == base[0]).all() and (ay == base[1]).all())}), flush=True)
     e.close()
