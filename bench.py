@@ -156,6 +156,15 @@ class Watchdog:
 REFERENCE_BUDGET_S = 150.0     # CPU time the whole reference arm may take (warm-up + timed steps)
 
 
+def bench_config(n_total, per_gpu, W, H):
+    """The `config` object of the JSON line: the workload only, so that both arms (this implementation and
+    --impl reference) print the SAME object for the same command line."""
+    return {"workload": f"{n_total}-body uniform 'C' cloud ({per_gpu} bodies per GPU), theta={THETA}, {W}x{H} window, G=80, dt=0.005, merge off",
+            "step": "PhysicsEngine.step(): 2 builds + 2 evaluations + KDK",
+            "l2": "no flush between steps: the per-step working set (~210 B/body of state, sort buffers and tree) exceeds the last-level "
+                  "cache (126 MB L2 on B200) and is rewritten by every build"}
+
+
 def run_reference(args, rank, world):
     """The reference's own CPU implementation of the path (JVM unavailable: the literal C++
     port in oracle/) on all host threads, same config/metric as the CUDA arm.  Every step is a
@@ -211,10 +220,9 @@ def run_reference(args, rank, world):
         "steps_per_s": args.steps / dt, "n_gpus": max(1, args.gpus), "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"{n_full}-body uniform 'C' cloud, theta={THETA}, {W}x{H} window, G=80, dt=0.005, merge off",
-                   "step": "PhysicsEngine.step(): 2 builds + 2 evaluations + KDK", "bodies_in_the_sample": len(scene[0])},
+        "config": bench_config(n_full, args.bodies, W, H),
         "cpu_baseline": {"value": val, "unit": "interactions/s", "cores": int(cores), "kind": "port",
-                         "sample": sample + " (C++ port of BarnesHutAlg.kt; no JVM in the image)"},
+                         "sample": sample + " (C++ port of BarnesHutAlg.kt; no JVM in the image)", "bodies_in_the_sample": len(scene[0])},
         "e2e": {"value": val, "unit": "interactions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "phases_ms_per_step": {"build": c["ms_build"] / args.steps, "walk": c["ms_walk"] / args.steps,
                                "integrate": c["ms_integrate"] / args.steps},
@@ -521,14 +529,12 @@ def main():
         "ms_per_step": dev_ms / args.steps, "wall_ms_per_step": wall / args.steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32 interactions, f64 state/COM/integrator", "data": "synthetic",
-        "config": {"workload": f"{n}-body uniform 'C' cloud ({args.bodies}/GPU), theta={THETA}, {W}x{H} window, G=80, dt=0.005, merge off",
-                   "step": "PhysicsEngine.step(): 2 builds + 2 evaluations + KDK",
-                   "parallelism": "single GPU" if n_gpus == 1 else (
-                       f"domain mode: {n_gpus} Morton ranges, local tree per rank + locally essential tree (all-reduced level summaries, "
-                       f"boundary subtrees {'read over NVLink peer memory (CUDA IPC)' if let_stats.get('enabled') == 2 else 'over NCCL send/recv'}), "
-                       f"re-homing every 8 steps" if let_stats and let_stats["let_evaluations"] > 0 else
-                       f"replicated tree, {n_gpus} Morton slices of targets, NCCL all-gather of positions"),
-                   "l2": "no flush: per-step working set (~210 B/body state+sort+tree) exceeds the 126 MB L2 and is rewritten every build"},
+        "config": bench_config(n, args.bodies, W, H),
+        "parallelism": "single GPU" if n_gpus == 1 else (
+            f"domain mode: {n_gpus} Morton ranges, local tree per rank + locally essential tree (all-reduced level summaries, "
+            f"boundary subtrees {'read over NVLink peer memory (CUDA IPC)' if let_stats.get('enabled') == 2 else 'over NCCL send/recv'}), "
+            f"re-homing every 8 steps" if let_stats and let_stats["let_evaluations"] > 0 else
+            f"replicated tree, {n_gpus} Morton slices of targets, NCCL all-gather of positions"),
         "interactions_per_step": inter / args.steps, "opened_per_step": opened / args.steps,
         "phases_ms_per_evaluation": {"build": build_ms, "walk": walk_ms},
         "ms_per_step_other": {"exchange": c["ms_comm"] / args.steps, "integrate_and_rest": c["ms_integrate"] / args.steps},

@@ -73,3 +73,21 @@ def test_watchdog_prints_the_line_and_leaves_when_a_phase_hangs(tmp_path):
     assert len(lines) == 1, r.stdout
     d = json.loads(lines[0])
     assert d["value"] == 1.0 and "stuck" in d["incomplete"]
+
+
+def test_reference_arm_prints_the_contract_line_with_the_same_config_object():
+    """`bench.py --impl reference`: the CPU arm on a small instance — same metric / unit / config object as the CUDA arm
+    prints for the same command line, a cpu_baseline describing the run, an e2e that repeats the line's value."""
+    import json
+    import subprocess
+    import sys
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--bodies", "20000", "--steps", "1", "--warmup", "0"],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    d = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
+    bench = _bench()
+    assert d["impl"] == "reference" and d["metric"] == "body_interactions_per_s" and d["unit"] == "interactions/s" and d["higher_is_better"] is True
+    assert set(d["config"]) == set(bench.bench_config(20000, 20000, 1, 1))            # the keys the CUDA arm prints
+    assert d["config"]["workload"].startswith("20000-body uniform") and "20000 bodies per GPU" in d["config"]["workload"]
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
