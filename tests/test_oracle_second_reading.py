@@ -136,3 +136,64 @@ def test_both_readings_of_the_reference_agree_bit_for_bit(oracle_lib, name, gen,
     if "merges" in name:
         assert o.n < len(scene[0]) - 40
     o.close()
+
+
+def _fuzz_scene(seed):
+    """tiny adversarial scenes: tight clusters (deep trees, jitter regime), exact duplicates, bodies on cell edges and
+    outside the box, zero and heavy masses, fast bodies"""
+    rng = np.random.default_rng(1000 + seed)
+    n = int(rng.integers(1, 60))
+    W, H = [(2400, 800), (800, 2400), (512, 512), (37, 91)][seed % 4]
+    half = max(W, H) / 2.0 + 2.0
+    x = rng.uniform(W / 2.0 - half, W / 2.0 + half, n)
+    y = rng.uniform(H / 2.0 - half, H / 2.0 + half, n)
+    k = int(rng.integers(0, n + 1))                       # a tight cluster
+    if k:
+        cx0, cy0 = rng.uniform(0.2 * W, 0.8 * W), rng.uniform(0.2 * H, 0.8 * H)
+        r = 10.0 ** rng.uniform(-6, 1)
+        x[:k], y[:k] = cx0 + rng.normal(0, r, k), cy0 + rng.normal(0, r, k)
+    for _ in range(int(rng.integers(0, 4))):              # exact duplicates
+        if n >= 2:
+            a, b = rng.integers(0, n, 2)
+            x[b], y[b] = x[a], y[a]
+    if n >= 3:                                            # on the cell edges / corners of the root and its children
+        x[n - 1], y[n - 1] = W / 2.0, H / 2.0
+        x[n - 2] = W / 2.0 - half
+        y[n - 3] = H / 2.0 + half                         # (the upper edge is outside: half-open)
+    if seed % 3 == 0 and n >= 4:
+        x[n - 4] = W / 2.0 + half + rng.uniform(0, 50)    # outside
+    vx, vy = rng.normal(0, 300, n), rng.normal(0, 300, n)
+    m = rng.choice([0.0, 0.5, 1.0, 3.0, 5000.0, 60000.0], n, p=[0.08, 0.3, 0.3, 0.2, 0.08, 0.04])
+    if seed % 2:
+        x, y = x.astype(np.float32).astype(np.float64), y.astype(np.float32).astype(np.float64)
+    return (x, y, vx, vy, m), W, H
+
+
+@pytest.mark.parametrize("seed", range(48))
+def test_fuzzed_tiny_scenes_agree_bit_for_bit(oracle_lib, seed):
+    scene, W, H = _fuzz_scene(seed)
+    theta = [0.0, 0.3, 0.5, 1.0, 1.6][seed % 5]
+    merge = [0.0, 8.0, 40.0][seed % 3]
+    _configure(W, H, theta, G=[80.0, 1.0, -5.0][seed % 3], dt=[0.005, 0.02, -0.005][seed % 3])
+    o = make_engine(oracle_lib, scene, W, H, theta=theta, merge_min_dist=merge, G=second.Config.G, dt=second.Config.DT)
+    bodies = _bodies(scene)
+    p = second.PhysicsEngine(bodies)
+    p.mergeMinDist = merge
+    originals = list(bodies)
+    # evaluation + cells (a jittering build moves bodies in both readings alike)
+    ax, ay = o.compute_accelerations()
+    root = p.build_tree()
+    p.compute_accelerations(root)
+    assert _same(p.ax[:len(bodies)], ax) and _same(p.ay[:len(bodies)], ay)
+    cells_o, cells_p = o.tree(), _cells(root, bodies)
+    for k in ("cx", "cy", "h", "mass", "comx", "comy"):
+        assert _same(cells_p[k], cells_o[k]), k
+    assert (np.array(cells_p["body"], np.int32) == cells_o["body"]).all()
+    for _ in range(3):
+        o.step(1)
+        p.step()
+        assert len(p.bodies) == o.n
+        for a, b in zip(_state(p.bodies), o.get_bodies()):
+            assert _same(a, b)
+    assert (np.array([originals.index(b) for b in p.bodies], np.int32) == o.get_origin()).all()
+    o.close()
