@@ -195,3 +195,40 @@ def test_closed_form_keys_on_cell_boundaries(oracle_lib, emul_lib):
     o.set_params(root_cx=1200.1, root_half=1000.3)
     g2 = emul_acc(emul_lib, scene, o.params, 0.5)
     assert g2["stats"][6] == 0
+
+
+@pytest.mark.parametrize("seed", range(48))
+def test_fuzzed_tiny_scenes_through_the_algorithm_core(oracle_lib, emul_lib, seed):
+    """The adversarial tiny scenes of tests/test_oracle_second_reading.py (tight clusters and exact duplicates in the
+    jitter regime, bodies on cell edges and outside the box, zero and heavy masses, four window shapes) through the
+    PRODUCT's algorithm core (bh_core.h on the host): mutated positions, dropped bodies, leaf depths, per-body
+    decisions and every visitQuads cell equal to the oracle's."""
+    from test_oracle_second_reading import _fuzz_scene
+    scene, W, H = _fuzz_scene(seed)
+    theta = [0.0, 0.3, 0.5, 1.0, 1.6][seed % 5]
+    o = make_engine(oracle_lib, scene, W, H, flags=1, theta=theta)
+    p = o.params
+    ax, ay = o.compute_accelerations()
+    ci, co = o.body_counts()
+    depth, path = leaf_paths(oracle_lib, o)
+    ox, oy, *_ = o.get_bodies()
+    x, y, vx, vy, m = (np.ascontiguousarray(a, np.float64) for a in scene)
+    n = len(x)
+    gx, gy, st = np.empty(n), np.empty(n), np.zeros(2, np.int64)
+    emul_lib.bh_emul_positions_after_build(n, _dp(x), _dp(y), _dp(m), C.c_double(p.root_cx), C.c_double(p.root_cy),
+                                           C.c_double(p.root_half), _dp(gx), _dp(gy), st.ctypes.data_as(I64))
+    assert st[1] == 0
+    assert (gx == ox).all() and (gy == oy).all()
+    cx, cy, h = p.root_cx, p.root_cy, p.root_half
+    outside = ~((x >= cx - h) & (x < cx + h) & (y >= cy - h) & (y < cy + h))           # BH.kt:61-62 on the ORIGINAL positions
+    assert st[0] == int((depth < 0).sum()) - int(outside.sum())                         # bodies the jitter replay pushed out of their cell
+    g = emul_acc(emul_lib, scene, p, theta)
+    assert (g["depth"] == depth).all()
+    assert (g["ci"] == ci).all() and (g["co"] == co).all()
+    ok = np.isfinite(ax)
+    assert (np.isnan(g["ax"]) == ~ok).all()
+    to = o.tree()
+    k, tg = emul_tree(emul_lib, scene, p, len(to["cx"]))
+    assert k == len(to["cx"])
+    for q in to:
+        assert (tg[q] == to[q]).all(), q
