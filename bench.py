@@ -42,8 +42,8 @@ def workload(n_gpus, bodies_per_gpu):
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons around the timed region (B200_PROFILING.md).  The query loop is started
     before the warm-up (nvidia-smi needs a few hundred ms to come up, longer with 8 ranks starting one each) and
-    its rows are time-stamped; the report uses the rows that fall inside the timed region widened by one sampling
-    period on either side (a 20-step region is shorter than the 100 ms period), else all rows, and says which."""
+    its rows are time-stamped; the report uses the rows that fall between the start of the timed region and one
+    sampling period after its end (a 20-step region is shorter than the 100 ms period), else all rows, and says which."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
     PERIOD = 0.1
@@ -85,8 +85,8 @@ class ClockSampler:
             self.proc.kill()
         rows = list(self.rows)
         t0 = self.t_begin if self.t_begin is not None else -1.0
-        near = [r for t, r in rows if t0 - self.PERIOD <= t <= t_stop + self.PERIOD]
-        window = "timed region +- one 100 ms sampling period"
+        near = [r for t, r in rows if t0 <= t <= t_stop + self.PERIOD + 0.05]
+        window = "from the start of the timed region to one 100 ms sampling period after its end"
         if not near:
             near, window = [r for _, r in rows], "whole run (no sample fell near the timed region)"
         sm = [float(r[1]) for r in near if len(r) >= 9 and r[1].replace(".", "").isdigit()]
@@ -466,9 +466,9 @@ def main():
     # ---- device-resident throughput: K steps, inputs already in HBM ------------------------
     sampler = ClockSampler(local_rank)
     sampler.start()
+    sampler.wait_ready()                            # (before the warm-up: no idle gap between warm-up and timed region)
     eng.step(args.warmup)
     eng.reset_counters()
-    sampler.wait_ready()
     barrier()
     sampler.begin()
     t0 = time.perf_counter()

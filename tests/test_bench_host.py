@@ -91,3 +91,23 @@ def test_reference_arm_prints_the_contract_line_with_the_same_config_object():
     assert d["config"]["workload"].startswith("20000-body uniform") and "20000 bodies per GPU" in d["config"]["workload"]
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+
+
+def test_clock_sampler_reports_rows_from_the_timed_region(tmp_path, monkeypatch):
+    """A stand-in `nvidia-smi` that takes 0.3 s to come up (8 ranks starting one each take longer) and prints a row every
+    100 ms: a 40 ms timed region still gets its samples, taken from its start to one period after its end."""
+    import stat
+    import time
+    fake = tmp_path / "nvidia-smi"
+    fake.write_text('#!/bin/bash\nsleep 0.3\nwhile true; do echo "0, 1830, 1965, 400.0, 0x4, Not Active, Not Active, Not Active, Active"; sleep 0.1; done\n')
+    fake.chmod(fake.stat().st_mode | stat.S_IEXEC)
+    monkeypatch.setenv("PATH", f"{tmp_path}:{os.environ['PATH']}")
+    bench = _bench()
+    s = bench.ClockSampler(0)
+    s.start()
+    s.wait_ready()
+    s.begin()
+    time.sleep(0.04)
+    r = s.stop()
+    assert r["samples"] >= 1 and r["sm_mhz"] == 1830.0 and r["sm_max_mhz"] == 1965.0 and r["reasons"] == ["sw_power_cap"], r
+    assert "timed region" in r["window"]
