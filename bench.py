@@ -549,67 +549,70 @@ def main():
 
     # ---- end to end through the C ABI with HOST buffers --------------------------------------
     wd.phase("end to end (host buffers through the C ABI)", 120)
-    e2e_steps = max(3, min(args.steps, 10))
-    if world == 1:
-        host = [torch.from_numpy(np.ascontiguousarray(a)).pin_memory() for a in scene]
-        hnp = [t.numpy() for t in host]
-        out = [torch.empty(n, dtype=torch.float64).pin_memory() for _ in range(5)]
-        onp = tuple(t.numpy() for t in out)
-        eng.step_io(1, inputs=hnp, out=onp)
-        eng.reset_counters()
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(e2e_steps):
-            # resetBodies(host arrays) + step() + getBodies(host arrays) in ONE C-ABI call: H2D of this
-            # step's inputs and D2H of its result are inside the call (and inside the timed region),
-            # overlapped with the compute where the data dependences allow (bh_step_io)
+    e2e = None
+    try:
+        e2e_steps = max(3, min(args.steps, 10))
+        if world == 1:
+            host = [torch.from_numpy(np.ascontiguousarray(a)).pin_memory() for a in scene]
+            hnp = [t.numpy() for t in host]
+            out = [torch.empty(n, dtype=torch.float64).pin_memory() for _ in range(5)]
+            onp = tuple(t.numpy() for t in out)
             eng.step_io(1, inputs=hnp, out=onp)
-        barrier()
-        e2e_wall = allmax(time.perf_counter() - t0)
-        e2e_inter = allsum(float(eng.counters()["total_interactions"]))
-        # the same three calls made separately (no overlap), for comparison
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(e2e_steps):
-            eng.set_bodies(*hnp)
-            eng.step(1)
-            eng.get_bodies(out=onp)
-        barrier()
-        seq_wall = allmax(time.perf_counter() - t0)
-        e2e = {"value": e2e_inter / e2e_wall, "unit": "interactions/s", "steps_per_s": e2e_steps / e2e_wall,
-               "h2d_bytes_per_step": 5 * 8 * n, "d2h_bytes_per_step": 5 * 8 * n, "steps": e2e_steps,
-               "api": "bh_step_io(1, host in, host out) per step: resetBodies + step + getBodies, pinned host arrays, copies overlapped with compute",
-               "steps_per_s_separate_calls": e2e_steps / seq_wall}
-    else:
-        # N > 1: SHARDED I/O — every rank moves only the bodies of its own slice (bh_step_io_slice): the slice's state goes
-        # up from pinned host memory, one step runs, the slice's new state comes down
-        # (like PhysicsEngine's own loop — getBodies, step, getBodies — the slice that comes down is the slice that goes
-        # up next: the host owns the state between steps, and bodies that migrated to another rank at a re-homing
-        # simply arrive in that rank's output)
-        hslice = [torch.empty(n, dtype=torch.float64).pin_memory().numpy() for _ in range(5)]
-        oslice = [torch.empty(n, dtype=torch.float64).pin_memory().numpy() for _ in range(5)]
-        k = eng.step_io_slice(0, out=hslice)                  # this rank's slice after the device-resident steps
-        k2 = eng.step_io_slice(1, inputs=[a[:k] for a in hslice], out=oslice)
-        hslice, oslice, k = oslice, hslice, k2
-        eng.reset_counters()
-        h2d = d2h = 0
-        epoch0 = eng.slice_epoch()
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(e2e_steps):
+            eng.reset_counters()
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(e2e_steps):
+                # resetBodies(host arrays) + step() + getBodies(host arrays) in ONE C-ABI call: H2D of this
+                # step's inputs and D2H of its result are inside the call (and inside the timed region),
+                # overlapped with the compute where the data dependences allow (bh_step_io)
+                eng.step_io(1, inputs=hnp, out=onp)
+            barrier()
+            e2e_wall = allmax(time.perf_counter() - t0)
+            e2e_inter = allsum(float(eng.counters()["total_interactions"]))
+            # the same three calls made separately (no overlap), for comparison
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(e2e_steps):
+                eng.set_bodies(*hnp)
+                eng.step(1)
+                eng.get_bodies(out=onp)
+            barrier()
+            seq_wall = allmax(time.perf_counter() - t0)
+            e2e = {"value": e2e_inter / e2e_wall, "unit": "interactions/s", "steps_per_s": e2e_steps / e2e_wall,
+                   "h2d_bytes_per_step": 5 * 8 * n, "d2h_bytes_per_step": 5 * 8 * n, "steps": e2e_steps,
+                   "api": "bh_step_io(1, host in, host out) per step: resetBodies + step + getBodies, pinned host arrays, copies overlapped with compute",
+                   "steps_per_s_separate_calls": e2e_steps / seq_wall}
+        else:
+            # N > 1: SHARDED I/O — every rank moves only the bodies of its own slice (bh_step_io_slice): the slice's state goes
+            # up from pinned host memory, one step runs, the slice's new state comes down
+            # (like PhysicsEngine's own loop — getBodies, step, getBodies — the slice that comes down is the slice that goes
+            # up next: the host owns the state between steps, and bodies that migrated to another rank at a re-homing
+            # simply arrive in that rank's output)
+            hslice = [torch.empty(n, dtype=torch.float64).pin_memory().numpy() for _ in range(5)]
+            oslice = [torch.empty(n, dtype=torch.float64).pin_memory().numpy() for _ in range(5)]
+            k = eng.step_io_slice(0, out=hslice)                  # this rank's slice after the device-resident steps
             k2 = eng.step_io_slice(1, inputs=[a[:k] for a in hslice], out=oslice)
-            h2d += 5 * 8 * k
-            d2h += 5 * 8 * k2
             hslice, oslice, k = oslice, hslice, k2
-        barrier()
-        e2e_wall = allmax(time.perf_counter() - t0)
-        e2e_inter = allsum(float(eng.counters()["total_interactions"]))
-        e2e = {"value": e2e_inter / e2e_wall, "unit": "interactions/s", "steps_per_s": e2e_steps / e2e_wall,
-               "h2d_bytes_per_step": allsum(float(h2d)) / e2e_steps, "d2h_bytes_per_step": allsum(float(d2h)) / e2e_steps, "steps": e2e_steps,
-               "api": "bh_step_io_slice(1, slice in, slice out) per step on every rank: only the rank's own bodies cross PCIe (pinned host arrays, "
-                      "transfers overlapped with the compute); the slice that comes down is the slice that goes up at the next step",
-               "re_homings_in_timed_region": eng.slice_epoch() - epoch0}
-
+            eng.reset_counters()
+            h2d = d2h = 0
+            epoch0 = eng.slice_epoch()
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(e2e_steps):
+                k2 = eng.step_io_slice(1, inputs=[a[:k] for a in hslice], out=oslice)
+                h2d += 5 * 8 * k
+                d2h += 5 * 8 * k2
+                hslice, oslice, k = oslice, hslice, k2
+            barrier()
+            e2e_wall = allmax(time.perf_counter() - t0)
+            e2e_inter = allsum(float(eng.counters()["total_interactions"]))
+            e2e = {"value": e2e_inter / e2e_wall, "unit": "interactions/s", "steps_per_s": e2e_steps / e2e_wall,
+                   "h2d_bytes_per_step": allsum(float(h2d)) / e2e_steps, "d2h_bytes_per_step": allsum(float(d2h)) / e2e_steps, "steps": e2e_steps,
+                   "api": "bh_step_io_slice(1, slice in, slice out) per step on every rank: only the rank's own bodies cross PCIe (pinned host arrays, "
+                          "transfers overlapped with the compute); the slice that comes down is the slice that goes up at the next step",
+                   "re_homings_in_timed_region": eng.slice_epoch() - epoch0}
+    except Exception as ex:                                       # (reported in the line; the headline stands)
+        e2e = {"value": None, "error": f"{type(ex).__name__}: {ex}"[:300]}
     line["e2e"] = e2e
 
     # ---- N > 1: the run checks itself (domain mode vs replicated tree vs one rank walking every body) -----------
@@ -617,11 +620,18 @@ def main():
     if world > 1:
         wd.phase("parity_check (domain mode vs replicated tree vs one rank walking every body)", 180)
         barrier()
-        pcheck = parity_check(eng, world, allsum, allmin)
+        try:
+            pcheck = parity_check(eng, world, allsum, allmin)
+        except Exception as ex:
+            pcheck = {"mode": "not checked: the check itself raised", "checked": False, "error": f"{type(ex).__name__}: {ex}"[:300],
+                      "interactions_equal": None, "acc_bit_identical": None}
         line["parity_check"] = pcheck
         if pcheck.get("checked") and not (pcheck["interactions_equal"] and pcheck["acc_bit_identical"]):
             line["parity_failed"] = True                         # a multi-GPU run that disagrees with itself: flagged at the top level
-    eng.close()
+    try:
+        eng.close()
+    except Exception:
+        pass
 
     # ---- BASELINE.json configs[2..4] at this GPU count (strong scaling: the total is fixed) --------------------
     cfg_records = line["configs"]
@@ -636,76 +646,79 @@ def main():
             torch.cuda.synchronize()
     wd.phase("side measurements (reuse mode, configs[0], direct sum, CPU baseline)", 300)
 
-    # ---- opt-in BH_FLAG_REUSE_ACC (result-identical, one evaluation per step): reported, not the headline
-    reuse = None
-    if world == 1:
-        er = bh_b200.NativeEngine(device=local_rank, capacity_hint=n, flags=bh_b200.BH_FLAG_REUSE_ACC)
-        er.set_window(W, H)
-        er.set_params(theta=THETA, merge_min_dist=0.0)
-        er.set_bodies(*scene)
-        er.step(args.warmup)
-        er.reset_counters()
-        er.step(args.steps)
-        cr = er.counters()
-        reuse = {"steps_per_s": args.steps / (cr["ms_step_call"] * 1e-3), "ms_per_step": cr["ms_step_call"] / args.steps,
-                 "evaluations_per_step": cr["total_evaluations"] / args.steps,
-                 "note": "step n+1 reuses a(t+dt) of step n (bit-identical state); not the reference's cost model, so not the headline"}
-        er.close()
-    line["reuse_acc_mode"] = reuse
+    try:
+        # ---- opt-in BH_FLAG_REUSE_ACC (result-identical, one evaluation per step): reported, not the headline
+        reuse = None
+        if world == 1:
+            er = bh_b200.NativeEngine(device=local_rank, capacity_hint=n, flags=bh_b200.BH_FLAG_REUSE_ACC)
+            er.set_window(W, H)
+            er.set_params(theta=THETA, merge_min_dist=0.0)
+            er.set_bodies(*scene)
+            er.step(args.warmup)
+            er.reset_counters()
+            er.step(args.steps)
+            cr = er.counters()
+            reuse = {"steps_per_s": args.steps / (cr["ms_step_call"] * 1e-3), "ms_per_step": cr["ms_step_call"] / args.steps,
+                     "evaluations_per_step": cr["total_evaluations"] / args.steps,
+                     "note": "step n+1 reuses a(t+dt) of step n (bit-identical state); not the reference's cost model, so not the headline"}
+            er.close()
+        line["reuse_acc_mode"] = reuse
 
-    # ---- BASELINE.json configs[0]: the reference's own scene (12,500 bodies, merge on) ---------
-    c1 = None
-    if rank == 0 and world == 1:
-        e1 = bh_b200.NativeEngine(device=local_rank)
-        e1.set_params(theta=THETA)                      # merge 4000 / 8 px stays on (reference default)
-        e1.set_bodies(*scenes_mod.snap_f32(scenes_mod.default_two_disks(seed=1)))
-        e1.step(20)
-        t0 = time.perf_counter()
-        e1.step(300)
-        c1 = {"workload": "reference two-disk scene, 12,500 bodies, theta=0.5, merge rule on", "steps_per_s": 300 / (time.perf_counter() - t0),
-              "bodies_left": e1.n}
-        e1.close()
-    line["configs0"] = c1
+        # ---- BASELINE.json configs[0]: the reference's own scene (12,500 bodies, merge on) ---------
+        c1 = None
+        if rank == 0 and world == 1:
+            e1 = bh_b200.NativeEngine(device=local_rank)
+            e1.set_params(theta=THETA)                      # merge 4000 / 8 px stays on (reference default)
+            e1.set_bodies(*scenes_mod.snap_f32(scenes_mod.default_two_disks(seed=1)))
+            e1.step(20)
+            t0 = time.perf_counter()
+            e1.step(300)
+            c1 = {"workload": "reference two-disk scene, 12,500 bodies, theta=0.5, merge rule on", "steps_per_s": 300 / (time.perf_counter() - t0),
+                  "bodies_left": e1.n}
+            e1.close()
+        line["configs0"] = c1
 
-    # ---- the device accuracy oracle (tiled all-pairs direct sum, BH.kt:250-259 over every pair): FP32-pipe roofline
-    direct = None
-    if rank == 0 and world == 1:
-        direct = []
-        for nd in (100_000, 1_000_000):
-            if nd > n:
-                continue
-            ed = bh_b200.NativeEngine(device=local_rank, capacity_hint=nd)
-            ed.set_window(W, H)
-            ed.set_params(theta=THETA, merge_min_dist=0.0)
-            ed.set_bodies(*[np.ascontiguousarray(a[:nd]) for a in scene])
-            ed.direct_sum()
-            ed.direct_sum()
-            ms = ed.counters()["ms_direct"]
-            tf = 14.0 * nd * (nd - 1) / (ms * 1e-3) / 1e12
-            direct.append({"kernel": "k_direct", "bodies": nd, "ms": ms, "pair_interactions_per_s": nd * (nd - 1) / (ms * 1e-3), "bound": "fp32",
-                           "achieved": tf, "peak": float(fp32[0]), "unit": "TFLOP/s", "frac": tf / float(fp32[0]) if fp32[0] > 0 else None,
-                           "algorithmic": "14 flop x N(N-1) pair interactions (SURVEY.md 8(d)); same measured FFMA peak as the walk"})
-            ed.close()
-    line["roofline_direct"] = direct
+        # ---- the device accuracy oracle (tiled all-pairs direct sum, BH.kt:250-259 over every pair): FP32-pipe roofline
+        direct = None
+        if rank == 0 and world == 1:
+            direct = []
+            for nd in (100_000, 1_000_000):
+                if nd > n:
+                    continue
+                ed = bh_b200.NativeEngine(device=local_rank, capacity_hint=nd)
+                ed.set_window(W, H)
+                ed.set_params(theta=THETA, merge_min_dist=0.0)
+                ed.set_bodies(*[np.ascontiguousarray(a[:nd]) for a in scene])
+                ed.direct_sum()
+                ed.direct_sum()
+                ms = ed.counters()["ms_direct"]
+                tf = 14.0 * nd * (nd - 1) / (ms * 1e-3) / 1e12
+                direct.append({"kernel": "k_direct", "bodies": nd, "ms": ms, "pair_interactions_per_s": nd * (nd - 1) / (ms * 1e-3), "bound": "fp32",
+                               "achieved": tf, "peak": float(fp32[0]), "unit": "TFLOP/s", "frac": tf / float(fp32[0]) if fp32[0] > 0 else None,
+                               "algorithmic": "14 flop x N(N-1) pair interactions (SURVEY.md 8(d)); same measured FFMA peak as the walk"})
+                ed.close()
+        line["roofline_direct"] = direct
 
-    # ---- CPU baseline beside it (rank 0, N = 1 only) ------------------------------------------
-    cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        lib = bh_b200.bind(os.path.join(ROOT, "oracle", "libbh_ref.so"))
-        o = bh_b200.NativeEngine(lib=lib)
-        o.set_window(W, H)
-        o.set_params(theta=THETA, merge_min_dist=0.0)
-        o.set_bodies(*scene)
-        o.reset_counters()
-        t0 = time.perf_counter()
-        o.step(2)
-        dt = time.perf_counter() - t0
-        oc = o.counters()
-        cpu = {"value": oc["total_interactions"] / dt, "unit": "interactions/s", "cores": int(lib.bh_ref_threads(o._h)),
-               "kind": "port", "steps_per_s": 2 / dt,
-               "sample": "2 full steps of the same 1M-body workload (C++ port of BarnesHutAlg.kt; the JVM reference cannot run in this image)"}
-        o.close()
-    line["cpu_baseline"] = cpu
+        # ---- CPU baseline beside it (rank 0, N = 1 only) ------------------------------------------
+        cpu = None
+        if rank == 0 and world == 1 and not args.no_cpu_baseline:
+            lib = bh_b200.bind(os.path.join(ROOT, "oracle", "libbh_ref.so"))
+            o = bh_b200.NativeEngine(lib=lib)
+            o.set_window(W, H)
+            o.set_params(theta=THETA, merge_min_dist=0.0)
+            o.set_bodies(*scene)
+            o.reset_counters()
+            t0 = time.perf_counter()
+            o.step(2)
+            dt = time.perf_counter() - t0
+            oc = o.counters()
+            cpu = {"value": oc["total_interactions"] / dt, "unit": "interactions/s", "cores": int(lib.bh_ref_threads(o._h)),
+                   "kind": "port", "steps_per_s": 2 / dt,
+                   "sample": "2 full steps of the same 1M-body workload (C++ port of BarnesHutAlg.kt; the JVM reference cannot run in this image)"}
+            o.close()
+        line["cpu_baseline"] = cpu
+    except Exception as ex:                                       # (what was measured so far is in the line)
+        line["side_measurements_error"] = f"{type(ex).__name__}: {ex}"[:300]
 
     wd.done()
     if rank == 0:
