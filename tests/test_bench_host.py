@@ -111,3 +111,28 @@ def test_clock_sampler_reports_rows_from_the_timed_region(tmp_path, monkeypatch)
     r = s.stop()
     assert r["samples"] >= 1 and r["sm_mhz"] == 1830.0 and r["sm_max_mhz"] == 1965.0 and r["reasons"] == ["sw_power_cap"], r
     assert "timed region" in r["window"]
+
+
+def test_bench_main_prints_one_contract_line():
+    """bench.py's main() end to end at world 1 over the oracle library (tests/bench_dry_run.py): ONE JSON line with every
+    key of the driver's contract, filled phase by phase."""
+    import json
+    import subprocess
+    import sys
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "bench_dry_run.py")], capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stderr[-3000:]
+    lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1, r.stdout[-2000:]
+    d = json.loads(lines[0])
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype",
+              "data", "config", "roofline", "cpu_baseline", "e2e", "gpu_launches", "clocks"):
+        assert k in d, k
+    assert d["metric"] == "body_interactions_per_s" and d["n_gpus"] == 1 and d["warmup"] >= 3 and d["vs_baseline"] is None
+    assert set(d["config"]) == {"workload", "step", "l2"}
+    for k in ("bound", "achieved", "peak", "unit", "frac", "traffic"):
+        assert k in d["roofline"], k
+    for k in ("value", "unit", "cores", "kind", "sample"):
+        assert k in d["cpu_baseline"], k
+    for k in ("value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"):
+        assert k in d["e2e"], k
+    assert d["e2e"]["h2d_bytes_per_step"] == 5 * 8 * 20000 and "incomplete" not in d and "side_measurement_errors" not in d
