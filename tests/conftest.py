@@ -102,7 +102,8 @@ ACC_FLOOR = 0.05       # uniform clouds: sum|a_ij| / |a_i| ~ 40 and some bodies 
                        # summed) is unbounded RELATIVE to |a_i|: there the gate is floor 0.05 for every body PLUS at
                        # most ACC_FRAC_ABOVE of the bodies above 1e-5 without any floor (measured 1.0e-4)
 ACC_FRAC_ABOVE = 2.0e-4
-H3_MEASURED = ("C1 two-disk 12.5k θ0.5", "10M two-disk")    # profiles/r02q_acc_error.json: max 3.1e-6 and 6.3e-7 with floor 1e-3
+H3_MEASURED = ("C1 two-disk 12.5k θ0.5",)                   # profiles/r02q_acc_error.json: max 3.1e-6 with floor 1e-3 on exactly this scene
+                                                             # (C3 on file too: 6.3e-7 on the bench's 10M merger, a variant of the test's scene)
 CLOUD_MEASURED = ("1M cloud",)                               # ibid.: 1.0e-4 of the bodies above 1e-5 unfloored, max 1.9e-4 with floor 1e-3
 
 
